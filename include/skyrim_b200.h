@@ -1,0 +1,108 @@
+/* skyrim_b200 — C-ABI of the B200-native step operators behind the Skyrim rollout path.
+ *
+ * The reference has no FFI of its own: its seam is the Python earth2mip ``TimeLoop``
+ * protocol consumed at
+ *   /root/reference/skyrim/core/models/utils.py:34-40   (for k,(time,output,_) in model(time,x))
+ *   /root/reference/skyrim/core/models/pangu.py:45-46   (pangu.load(registry.get_model(...)))
+ *   /root/reference/skyrim/core/models/fourcastnet_v2.py:36-37
+ * Each entry point below replaces what one of those call sites reaches inside the
+ * ONNXRuntime / earth2mip back-ends.  Plain pointers and sizes only; no Python or torch
+ * types cross this boundary.  Device pointers are raw CUDA device addresses (the Python
+ * host passes ``tensor.data_ptr()``), ``stream`` is a ``cudaStream_t`` cast to void*.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (never exits);
+ * sky_last_error() returns a thread-local message.  A handle is bound to one device and is
+ * not thread-safe; distinct handles on distinct devices may be driven concurrently.
+ * The caller owns state / workspace buffers; the engine owns its device weights.
+ */
+#ifndef SKYRIM_B200_H
+#define SKYRIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKY_ABI_VERSION 1
+
+enum { SKY_MODEL_PANGU6 = 1, SKY_MODEL_SFNO73 = 2 };
+enum { SKY_OK = 0, SKY_ERR_ARG = -1, SKY_ERR_CUDA = -2, SKY_ERR_STATE = -3, SKY_ERR_NOMEM = -4 };
+
+/* Pangu-Weather 6-h operator shape (patch (2,4,4) and window (2,6,12) are fixed).
+ * Replaces the shape information baked into pangu_weather_6.onnx (pangu.py:46). */
+typedef struct {
+  int32_t nlat, nlon;      /* 721, 1440 */
+  int32_t n_levels;        /* 13 */
+  int32_t dim;             /* 192 */
+  int32_t depths[4];       /* 2,6,6,2 */
+  int32_t heads[4];        /* 6,12,12,6 */
+  float ln_eps;            /* 1e-5 */
+  float mask_value;        /* -100 */
+} sky_pangu_config_t;
+
+/* SFNO (FourCastNet-v2-small) operator shape; replaces the hyper-parameters read from the
+ * fcnv2_sm checkpoint (fourcastnet_v2.py:37). */
+typedef struct {
+  int32_t nlat, nlon;      /* 721, 1440 */
+  int32_t n_channels;      /* 73 */
+  int32_t embed;           /* 384 */
+  int32_t layers;          /* 8 */
+  int32_t scale_factor;    /* 3 */
+  int32_t mlp_ratio;       /* 2 */
+  float eps;               /* instance-norm epsilon */
+} sky_sfno_config_t;
+
+/* one named fp32 tensor inside a flat weight arena */
+typedef struct {
+  char name[96];
+  uint64_t offset;         /* in floats from the arena start */
+  uint64_t count;          /* number of floats */
+} sky_param_desc_t;
+
+typedef struct sky_model sky_model_t;
+
+int sky_abi_version(void);
+const char* sky_last_error(void);
+
+/* model_kind: SKY_MODEL_*; cfg points at the matching sky_*_config_t. */
+int sky_model_create(sky_model_t** out, int model_kind, const void* cfg, size_t cfg_bytes, int device);
+
+/* Load (copy + repack for the tensor cores) the fp32 weight arena.  `arena` is a host
+ * pointer (arena_on_device = 0) or a device pointer on the model's device (= 1, e.g. the
+ * buffer that received the one-time NCCL broadcast).  The caller keeps ownership.
+ * Replaces ONNX initialiser loading / torch.load in the reference back-ends. */
+int sky_model_load_weights(sky_model_t* m, const float* arena, uint64_t n_floats,
+                           const sky_param_desc_t* manifest, int32_t n_params, int32_t arena_on_device,
+                           void* stream);
+
+/* scratch bytes one step needs for `batch` members */
+size_t sky_model_workspace_bytes(const sky_model_t* m, int32_t batch);
+
+/* One 6-h step for `batch` independent members: x_in, x_out are device fp32
+ * (batch, C, nlat, nlon), may not alias.  Asynchronous and stream-ordered; no host sync.
+ * Replaces one `next()` of the TimeLoop generator (utils.py:34). */
+int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batch, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Intermediate tensor taps for kernel-level parity tests: after a step, copy the named
+ * internal buffer ("embed"/"tokens1"/"tokens2"...) of the LAST step into dst (device fp32). */
+int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* workspace,
+                         int32_t batch, void* stream);
+
+/* x[m, c, :, :] += amp * sigma[c] * N(0,1), Philox4x32-10 keyed by (seed, member0 + m):
+ * perturbed-IC ensemble members (new functionality; the reference's only perturbation
+ * helper is the single-point edit at models/utils.py:70-92). */
+int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int32_t member0,
+                   int32_t members, int32_t channels, int64_t plane, void* stream);
+
+/* how many kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t sky_launch_count(void);
+
+int sky_model_destroy(sky_model_t* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYRIM_B200_H */

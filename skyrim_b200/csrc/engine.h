@@ -1,0 +1,48 @@
+// Host-side engine interface shared by the per-model translation units and the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+
+#include "../../include/skyrim_b200.h"
+
+namespace sky {
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void set_error(const char* fmt, ...);
+
+struct ParamView {
+  const float* dev;  // device pointer inside the resident fp32 arena
+  uint64_t count;
+};
+
+// Base class of a step operator bound to one device.
+struct Engine {
+  int device = 0;
+  int num_sms = 148;
+  float* arena = nullptr;  // resident fp32 copy of the weight arena
+  uint64_t arena_floats = 0;
+  std::map<std::string, ParamView> params;
+  bool loaded = false;
+
+  virtual ~Engine();
+  int load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,
+                 int on_device, cudaStream_t st);
+  const float* param(const char* name, uint64_t expect_count);  // nullptr + error if missing / wrong size
+
+  virtual int prepare(cudaStream_t st) = 0;  // repack weights after load_arena
+  virtual size_t workspace_bytes(int batch) const = 0;
+  virtual int step(const float* x_in, float* x_out, int batch, void* ws, size_t ws_bytes, cudaStream_t st) = 0;
+  virtual int debug_copy(const char* what, float* dst, uint64_t max_floats, void* ws, int batch,
+                         cudaStream_t st) = 0;
+};
+
+Engine* make_pangu_engine(const sky_pangu_config_t& cfg, int device);
+Engine* make_sfno_engine(const sky_sfno_config_t& cfg, int device);
+
+}  // namespace sky

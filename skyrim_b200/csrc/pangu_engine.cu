@@ -1,0 +1,387 @@
+// Pangu-Weather 6-h step operator on sm_100a: weight repacking + the per-step kernel
+// sequence.  Replaces what /root/reference/skyrim/core/models/pangu.py:45-46 loads
+// (two ONNXRuntime sessions) and what utils.py:34 steps.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "attention.cuh"
+#include "engine.h"
+#include "gemm_ref.cuh"
+#include "gemm_tc.cuh"
+
+namespace sky {
+
+// ======================================================================================
+// weight repacking (runs once, at load)
+// ======================================================================================
+// fp32 W (logical [N, K]; stored [N,K] or, if transposed, [K,N]) ->
+//   plain fp16 [N, Kp]  and  tile image [N/BN][Kp/64][BN rows x 128 B, SWIZZLE_128B]
+__global__ void k_pack_weight(const float* __restrict__ W, int N, int K, int Kp, int BN, int transposed,
+                              __half* __restrict__ plain, uint8_t* __restrict__ img) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-half chunk each
+  int chunks_per_row = Kp / 8;
+  if (idx >= (long long)N * chunks_per_row) return;
+  int n = (int)(idx / chunks_per_row), kc = (int)(idx % chunks_per_row);
+  __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    int k = kc * 8 + e;
+    float v = 0.f;
+    if (k < K) v = transposed ? W[(long long)k * N + n] : W[(long long)n * K + k];
+    h[e] = __float2half_rn(v);
+  }
+  uint4 pk = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(plain + (long long)n * Kp + kc * 8) = pk;
+  int nt = n / BN, nr = n % BN, kb = kc / 8, ch = kc % 8;
+  size_t tile = ((size_t)nt * (Kp / 64) + kb) * (size_t)BN * 128;
+  *reinterpret_cast<uint4*>(img + tile + sw128_offset(nr, ch)) = pk;
+}
+
+// earth-specific bias (3312, n_type, heads) -> (n_type, heads, 3312)
+__global__ void k_pack_bias_table(const float* __restrict__ src, float* __restrict__ dst, int L, int n_type,
+                                  int heads) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)L * n_type * heads;
+  if (idx >= tot) return;
+  int l = (int)(idx % L);
+  long long th = idx / L;  // type*heads + head
+  dst[idx] = src[(long long)l * n_type * heads + th];
+}
+
+// DownSample front end: 2x2 (lat, lon) merge + zero pad + LayerNorm(4C) -> fp16 rows.
+// One warp per output row; NPL = (4C)/32 values per lane.
+template <int NPL>
+__global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__ x, __half* __restrict__ out,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int Z, int H,
+                                                       int W, int C, int H2, int W2, long long rows) {
+  long long row = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  int w2 = (int)(row % W2); long long q = row / W2;
+  int h2 = (int)(q % H2); q /= H2;  // q = member*Z + z
+  float v[NPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    int e = lane + 32 * i;  // feature index in (hs, ws, c)
+    int sub = e / C, c = e % C;
+    int h = 2 * h2 + (sub >> 1), w = 2 * w2 + (sub & 1);
+    v[i] = h < H ? x[((q * H + h) * W + w) * C + c] : 0.f;
+    s += v[i];
+  }
+  float mean = warp_sum(s) / (NPL * 32);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) { float d = v[i] - mean; ss += d * d; }
+  float rstd = rsqrtf(warp_sum(ss) / (NPL * 32) + eps);
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    int e = lane + 32 * i;
+    out[row * (NPL * 32) + e] = __float2half_rn((v[i] - mean) * rstd * gamma[e] + beta[e]);
+  }
+}
+
+// ======================================================================================
+// engine
+// ======================================================================================
+struct GemmW {
+  uint8_t* img = nullptr;
+  __half* plain = nullptr;
+  int N = 0, K = 0, Kp = 0, BN = 0;
+};
+struct BlockW {
+  GemmW qkv, proj, fc1, fc2;
+  const float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float* bias_tab;  // (n_type, heads, 3312)
+};
+
+struct PanguEngine : Engine {
+  sky_pangu_config_t cfg;
+  Geo g1, g2;
+  int nch, nup;
+  bool use_ref = false;
+  std::vector<void*> owned;
+  GemmW embed_u, embed_s, down, up1, up2, rec_u, rec_s;
+  std::vector<BlockW> blocks[4];
+  const float *mean, *stdv, *masks, *embed_u_b, *embed_s_b, *down_g, *down_b, *up_g, *up_b, *rec_u_b, *rec_s_b;
+
+  PanguEngine(const sky_pangu_config_t& c, int dev) : cfg(c) {
+    device = dev;
+    nup = 5 * c.n_levels;
+    nch = nup + 4;
+    auto mk = [&](int H, int W, int C, int heads) {
+      Geo g;
+      g.Z = (c.n_levels + 1) / 2 + 1;
+      g.H = H; g.W = W; g.C = C;
+      g.Hp = (H + WH - 1) / WH * WH;
+      g.nWz = g.Z / WZ; g.nWh = g.Hp / WH; g.nWw = W / WW;
+      g.T = g.Z * H * W; g.nWin = g.nWz * g.nWh * g.nWw; g.heads = heads;
+      return g;
+    };
+    int H = (c.nlat + 3) / 4, W = c.nlon / 4;
+    g1 = mk(H, W, c.dim, c.heads[0]);
+    g2 = mk((H + 1) / 2, W / 2, 2 * c.dim, c.heads[1]);
+    const char* e = getenv("SKY_GEMM");
+    use_ref = e && !strcmp(e, "ref");
+  }
+  ~PanguEngine() override {
+    for (void* p : owned) cudaFree(p);
+  }
+
+  template <class T>
+  T* dalloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", n * sizeof(T)); return nullptr; }
+    owned.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+
+  int pack(GemmW& g, const char* name, int N, int K, int BN, bool transposed, cudaStream_t st) {
+    const float* w = param(name, (uint64_t)N * K);
+    if (!w) return SKY_ERR_ARG;
+    g.N = N; g.K = K; g.Kp = (K + 63) / 64 * 64; g.BN = BN;
+    if (N % BN) { set_error("%s: N=%d not a multiple of BLOCK_N=%d", name, N, BN); return SKY_ERR_ARG; }
+    g.plain = dalloc<__half>((size_t)N * g.Kp);
+    g.img = dalloc<uint8_t>((size_t)N * g.Kp * 2);
+    if (!g.plain || !g.img) return SKY_ERR_NOMEM;
+    long long chunks = (long long)N * g.Kp / 8;
+    k_pack_weight<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(w, N, K, g.Kp, BN, transposed ? 1 : 0, g.plain, g.img);
+    count_launch();
+    SKY_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+
+  int prepare(cudaStream_t st) override {
+    const int C = cfg.dim;
+#define P(dst, name, cnt) if (!((dst) = param(name, (uint64_t)(cnt)))) return SKY_ERR_ARG;
+    P(mean, "norm.mean", nch); P(stdv, "norm.std", nch);
+    P(masks, "const.masks", 3LL * cfg.nlat * cfg.nlon);
+    P(embed_u_b, "embed.upper.b", C); P(embed_s_b, "embed.surf.b", C);
+    P(down_g, "down.ln.g", 4 * C); P(down_b, "down.ln.b", 4 * C);
+    P(up_g, "up.ln.g", C); P(up_b, "up.ln.b", C);
+    P(rec_u_b, "recover.upper.b", 5); P(rec_s_b, "recover.surf.b", 4);
+    int rc;
+    if ((rc = pack(embed_u, "embed.upper.w", C, 160, 192, false, st))) return rc;
+    if ((rc = pack(embed_s, "embed.surf.w", C, 112, 192, false, st))) return rc;
+    if ((rc = pack(down, "down.w", 2 * C, 4 * C, 192, false, st))) return rc;
+    if ((rc = pack(up1, "up.w1", 4 * C, 2 * C, 192, false, st))) return rc;
+    if ((rc = pack(up2, "up.w2", C, C, 192, false, st))) return rc;
+    if ((rc = pack(rec_u, "recover.upper.w", 160, 2 * C, 160, true, st))) return rc;
+    if ((rc = pack(rec_s, "recover.surf.w", 64, 2 * C, 64, true, st))) return rc;
+    for (int li = 0; li < 4; ++li) {
+      const Geo& g = (li == 0 || li == 3) ? g1 : g2;
+      const int c = g.C, heads = cfg.heads[li], n_type = g.nWz * g.nWh;
+      blocks[li].resize(cfg.depths[li]);
+      for (int bi = 0; bi < cfg.depths[li]; ++bi) {
+        BlockW& b = blocks[li][bi];
+        char nm[96];
+        auto N = [&](const char* s) { snprintf(nm, sizeof nm, "layer%d.block%d.%s", li, bi, s); return nm; };
+        if ((rc = pack(b.qkv, N("qkv.w"), 3 * c, c, 192, false, st))) return rc;
+        if ((rc = pack(b.proj, N("proj.w"), c, c, c, false, st))) return rc;
+        if ((rc = pack(b.fc1, N("fc1.w"), 4 * c, c, 192, false, st))) return rc;
+        if ((rc = pack(b.fc2, N("fc2.w"), c, 4 * c, c, false, st))) return rc;
+        P(b.qkv_b, N("qkv.b"), 3 * c); P(b.proj_b, N("proj.b"), c);
+        P(b.fc1_b, N("fc1.b"), 4 * c); P(b.fc2_b, N("fc2.b"), c);
+        P(b.ln1_g, N("ln1.g"), c); P(b.ln1_b, N("ln1.b"), c);
+        P(b.ln2_g, N("ln2.g"), c); P(b.ln2_b, N("ln2.b"), c);
+        const float* bt;
+        long long tot = (long long)ATT_TABLE * n_type * heads;
+        P(bt, N("bias_table"), tot);
+        b.bias_tab = dalloc<float>((size_t)tot);
+        if (!b.bias_tab) return SKY_ERR_NOMEM;
+        k_pack_bias_table<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(bt, b.bias_tab, ATT_TABLE, n_type, heads);
+        count_launch();
+      }
+    }
+#undef P
+    SKY_CUDA_OK(cudaGetLastError());
+    SKY_CUDA_OK(cudaFuncSetAttribute(k_window_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    SKY_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+  }
+
+  // ---- workspace carving -----------------------------------------------------------------
+  struct Ws {
+    float *x1, *skip, *x2, *scratch;
+    __half *qkv, *att, *hid;
+    size_t total;
+  };
+  Ws carve(void* base, int B) const {
+    Ws w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return (char*)base + o; };
+    const size_t C = cfg.dim;
+    size_t rows_win1 = (size_t)B * g1.nWin * WIN_TOK, rows_win2 = (size_t)B * g2.nWin * WIN_TOK;
+    size_t qkv_el = rows_win1 * 3 * C > rows_win2 * 6 * C ? rows_win1 * 3 * C : rows_win2 * 6 * C;
+    size_t hid_el = (size_t)B * g1.T * 4 * C;  // >= B*T2*8C, B*T2*4C (down), B*T1*C (up)
+    w.x1 = (float*)take((size_t)B * g1.T * C * 4);
+    w.skip = (float*)take((size_t)B * g1.T * C * 4);
+    w.x2 = (float*)take((size_t)B * g2.T * 2 * C * 4);
+    w.qkv = (__half*)take(qkv_el * 2);
+    w.att = (__half*)take(qkv_el / 3 * 2);
+    w.hid = (__half*)take(hid_el * 2);
+    size_t scr = 0;
+    if (use_ref) {
+      scr = rows_win1 * 3 * C;
+      if (hid_el > scr) scr = hid_el;
+      scr *= 4;
+    }
+    w.scratch = (float*)take(scr);
+    w.total = off;
+    return w;
+  }
+  size_t workspace_bytes(int batch) const override { return carve(nullptr, batch).total; }
+
+  // ---- GEMM dispatch -----------------------------------------------------------------------
+  template <int BN, class Prod, class Epi>
+  int gemm(const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
+    if (w.BN != BN) { set_error("internal: weight packed for BLOCK_N=%d used with %d", w.BN, BN); return SKY_ERR_STATE; }
+    if (use_ref) {
+      count_launch(2);
+      return launch_gemm_ref(prod, epi, w.plain, scratch, M, w.N, w.Kp, BN, st);
+    }
+    count_launch();
+    return launch_gemm_tc<Prod, Epi, BN>(prod, epi, w.img, M, w.N, w.Kp, num_sms, st);
+  }
+
+  int run_block(float* x, const Geo& g, const BlockW& b, int roll, int B, const Ws& ws, cudaStream_t st) {
+    const int C = g.C;
+    const long long Mw = (long long)B * g.nWin * WIN_TOK, Mt = (long long)B * g.T;
+    int rc;
+    {
+      ProdWindow p{x, g, roll, Mw};
+      EpiStoreF16<false> e{ws.qkv, 3 * C, b.qkv_b, Mw};
+      if ((rc = gemm<192>(p, e, b.qkv, Mw, ws.scratch, st))) return rc;
+    }
+    {
+      dim3 grid(g.heads, (unsigned)(B * g.nWin));
+      k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.att, b.bias_tab, g, roll,
+                                                                  rsqrtf(32.f), cfg.mask_value);
+      count_launch();
+      SKY_CUDA_OK(cudaGetLastError());
+    }
+    {
+      ProdPlainF16 p{ws.att, C, Mw, C};
+      EpiLnResidual e{x, C, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps, Mw, 1, g, roll};
+      rc = C == 192 ? gemm<192>(p, e, b.proj, Mw, ws.scratch, st) : gemm<384>(p, e, b.proj, Mw, ws.scratch, st);
+      if (rc) return rc;
+    }
+    {
+      ProdPlainF32 p{x, C, Mt, C};
+      EpiStoreF16<true> e{ws.hid, 4 * C, b.fc1_b, Mt};
+      if ((rc = gemm<192>(p, e, b.fc1, Mt, ws.scratch, st))) return rc;
+    }
+    {
+      ProdPlainF16 p{ws.hid, 4 * C, Mt, 4 * C};
+      EpiLnResidual e{x, C, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps, Mt, 0, g, 0};
+      rc = C == 192 ? gemm<192>(p, e, b.fc2, Mt, ws.scratch, st) : gemm<384>(p, e, b.fc2, Mt, ws.scratch, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+
+  int step(const float* x_in, float* x_out, int B, void* wsp, size_t ws_bytes, cudaStream_t st) override {
+    if (!loaded) { set_error("weights not loaded"); return SKY_ERR_STATE; }
+    if (cfg.dim != 192) { set_error("engine kernels are instantiated for dim=192 (got %d)", cfg.dim); return SKY_ERR_ARG; }
+    Ws ws = carve(wsp, B);
+    if (ws_bytes < ws.total) { set_error("workspace too small: %zu < %zu", ws_bytes, ws.total); return SKY_ERR_ARG; }
+    const int C = cfg.dim, HW = g1.H * g1.W, nzt = g1.Z - 1;
+    int rc;
+    // test tap: SKY_STOP_AFTER=<stage> returns early so debug_copy can read the token buffers
+    // (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3)
+    const char* stop_env = getenv("SKY_STOP_AFTER");
+    const int stop = stop_env ? atoi(stop_env) : 99;
+    // ---- patch embedding ----
+    {
+      long long M = (long long)B * nzt * HW;
+      ProdEmbedUpper p{x_in, mean, stdv, cfg.nlat, cfg.nlon, cfg.n_levels, 5, nch, g1.H, g1.W, nzt, M};
+      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW};
+      if ((rc = gemm<192>(p, e, embed_u, M, ws.scratch, st))) return rc;
+      long long Ms = (long long)B * HW;
+      ProdEmbedSurf ps{x_in, masks, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 4, 3, g1.H, g1.W, Ms};
+      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW};
+      if ((rc = gemm<192>(ps, es, embed_s, Ms, ws.scratch, st))) return rc;
+    }
+    if (stop == 0) return 0;
+    // ---- layer 0 ----
+    for (size_t i = 0; i < blocks[0].size(); ++i)
+      if ((rc = run_block(ws.x1, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
+    if (stop == 1) return 0;
+    SKY_CUDA_OK(cudaMemcpyAsync(ws.skip, ws.x1, (size_t)B * g1.T * C * 4, cudaMemcpyDeviceToDevice, st));
+    // ---- down-sample ----
+    {
+      long long rows = (long long)B * g2.T;
+      k_down_merge_ln<24><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ws.x1, ws.hid, down_g, down_b, cfg.ln_eps, g1.Z,
+                                                                   g1.H, g1.W, C, g2.H, g2.W, rows);
+      count_launch();
+      SKY_CUDA_OK(cudaGetLastError());
+      ProdPlainF16 p{ws.hid, 4 * C, rows, 4 * C};
+      EpiStoreF32 e{ws.x2, 2 * C, nullptr, rows, 0, 0, 0, 0};
+      if ((rc = gemm<192>(p, e, down, rows, ws.scratch, st))) return rc;
+    }
+    if (stop == 2) return 0;
+    for (int li = 1; li <= 2; ++li) {
+      for (size_t i = 0; i < blocks[li].size(); ++i)
+        if ((rc = run_block(ws.x2, g2, blocks[li][i], (int)(i & 1), B, ws, st))) return rc;
+      if (stop == 2 + li) return 0;
+    }
+    // ---- up-sample ----
+    {
+      long long rows = (long long)B * g2.T;
+      ProdPlainF32 p{ws.x2, 2 * C, rows, 2 * C};
+      EpiUpShuffleLn e{ws.hid, C, up_g, up_b, cfg.ln_eps, rows, g1.Z, g1.H, g1.W, g2.H, g2.W};
+      if ((rc = gemm<192>(p, e, up1, rows, ws.scratch, st))) return rc;
+      long long M = (long long)B * g1.T;
+      ProdPlainF16 p2{ws.hid, C, M, C};
+      EpiStoreF32 e2{ws.x1, C, nullptr, M, 0, 0, 0, 0};
+      if ((rc = gemm<192>(p2, e2, up2, M, ws.scratch, st))) return rc;
+    }
+    if (stop == 5) return 0;
+    for (size_t i = 0; i < blocks[3].size(); ++i)
+      if ((rc = run_block(ws.x1, g1, blocks[3][i], (int)(i & 1), B, ws, st))) return rc;
+    if (stop == 6) return 0;
+    // ---- patch recovery ----
+    {
+      long long M = (long long)B * nzt * HW;
+      ProdConcat p{ws.skip, ws.x1, C, g1.T, HW, 1, nzt, M};
+      EpiRecover e{x_out, rec_u_b, mean, stdv, cfg.nlat, cfg.nlon, nch, 0, cfg.n_levels, 2, g1.H, g1.W, nzt, 160, M};
+      if ((rc = gemm<160>(p, e, rec_u, M, ws.scratch, st))) return rc;
+      long long Ms = (long long)B * HW;
+      ProdConcat ps{ws.skip, ws.x1, C, g1.T, HW, 0, 1, Ms};
+      EpiRecover es{x_out, rec_s_b, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 1, 1, g1.H, g1.W, 1, 64, Ms};
+      if ((rc = gemm<64>(ps, es, rec_s, Ms, ws.scratch, st))) return rc;
+    }
+    return 0;
+  }
+
+  int debug_copy(const char* what, float* dst, uint64_t max_floats, void* wsp, int B, cudaStream_t st) override {
+    Ws ws = carve(wsp, B);
+    const float* src = nullptr;
+    uint64_t n = 0;
+    if (!strcmp(what, "tokens1")) { src = ws.x1; n = (uint64_t)B * g1.T * cfg.dim; }
+    else if (!strcmp(what, "skip")) { src = ws.skip; n = (uint64_t)B * g1.T * cfg.dim; }
+    else if (!strcmp(what, "tokens2")) { src = ws.x2; n = (uint64_t)B * g2.T * 2 * cfg.dim; }
+    else { set_error("unknown debug buffer '%s'", what); return SKY_ERR_ARG; }
+    if (n > max_floats) n = max_floats;
+    SKY_CUDA_OK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+};
+
+Engine* make_pangu_engine(const sky_pangu_config_t& cfg, int device) {
+  if (cfg.nlon % 96 || cfg.nlat < 8 || cfg.n_levels != 13 || cfg.dim != 192) {
+    set_error("unsupported Pangu shape: nlat=%d nlon=%d (need nlon %% 96 == 0) levels=%d dim=%d", cfg.nlat, cfg.nlon,
+              cfg.n_levels, cfg.dim);
+    return nullptr;
+  }
+  for (int i = 0; i < 4; ++i) {
+    int c = (i == 0 || i == 3) ? cfg.dim : 2 * cfg.dim;
+    if (cfg.heads[i] * 32 != c) { set_error("head_dim must be 32"); return nullptr; }
+  }
+  return new PanguEngine(cfg, device);
+}
+
+}  // namespace sky

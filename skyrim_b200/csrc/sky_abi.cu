@@ -1,0 +1,193 @@
+// C-ABI entry points (include/skyrim_b200.h) + engine base plumbing + IC perturbation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "engine.h"
+#include "sky_common.cuh"
+
+namespace sky {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+Engine::~Engine() {
+  if (arena) cudaFree(arena);
+}
+
+int Engine::load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,
+                       int on_device, cudaStream_t st) {
+  SKY_CUDA_OK(cudaSetDevice(device));
+  if (arena) { cudaFree(arena); arena = nullptr; }
+  SKY_CUDA_OK(cudaMalloc(&arena, n_floats * sizeof(float)));
+  arena_floats = n_floats;
+  SKY_CUDA_OK(cudaMemcpyAsync(arena, src, n_floats * sizeof(float),
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  params.clear();
+  for (int i = 0; i < n_params; ++i) {
+    const sky_param_desc_t& d = manifest[i];
+    if (d.offset + d.count > n_floats) { set_error("param %s exceeds the arena", d.name); return SKY_ERR_ARG; }
+    if (d.offset % 4) { set_error("param %s is not 16-byte aligned in the arena", d.name); return SKY_ERR_ARG; }
+    char nm[97];
+    memcpy(nm, d.name, 96); nm[96] = 0;
+    params[nm] = ParamView{arena + d.offset, d.count};
+  }
+  int rc = prepare(st);
+  if (rc) return rc;
+  loaded = true;
+  return 0;
+}
+
+const float* Engine::param(const char* name, uint64_t expect) {
+  auto it = params.find(name);
+  if (it == params.end()) { set_error("missing parameter '%s'", name); return nullptr; }
+  if (it->second.count != expect) {
+    set_error("parameter '%s' has %llu floats, expected %llu", name, (unsigned long long)it->second.count,
+              (unsigned long long)expect);
+    return nullptr;
+  }
+  return it->second.dev;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 Gaussian perturbation (K11)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// each thread perturbs 4 consecutive floats of one (member, channel) plane
+__global__ void k_perturb_ic(float* __restrict__ x, const float* __restrict__ sigma, float amp, uint64_t seed,
+                             int member0, int channels, long long plane, long long n_quads_per_plane,
+                             long long total_quads) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total_quads) return;
+  long long pc = q / n_quads_per_plane, qi = q % n_quads_per_plane;  // pc = member*channels + c
+  int c = (int)(pc % channels);
+  int member = member0 + (int)(pc / channels);
+  uint32_t ctr[4] = {(uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)c, (uint32_t)member};
+  philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  // Box-Muller on two pairs
+  const float s = amp * sigma[c];
+  float u0 = ((float)ctr[0] + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)ctr[1] + 0.5f) * 2.3283064365386963e-10f;
+  float u2 = ((float)ctr[2] + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)ctr[3] + 0.5f) * 2.3283064365386963e-10f;
+  float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float z[4];
+  __sincosf(6.283185307179586f * u1, &z[1], &z[0]);
+  __sincosf(6.283185307179586f * u3, &z[3], &z[2]);
+  z[0] *= r0; z[1] *= r0; z[2] *= r1; z[3] *= r1;
+  long long base = pc * plane + qi * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (qi * 4 + e < plane) x[base + e] += s * z[e];
+}
+
+}  // namespace sky
+
+using namespace sky;
+
+struct sky_model {
+  Engine* eng;
+};
+
+extern "C" {
+
+int sky_abi_version(void) { return SKY_ABI_VERSION; }
+const char* sky_last_error(void) { return g_err; }
+uint64_t sky_launch_count(void) { return g_launches.load(); }
+
+int sky_model_create(sky_model_t** out, int kind, const void* cfg, size_t cfg_bytes, int device) {
+  if (!out || !cfg) { set_error("null argument"); return SKY_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device visible: the skyrim_b200 engine has no CPU fallback");
+    return SKY_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device %d out of range (%d visible)", device, ndev); return SKY_ERR_ARG; }
+  SKY_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SKY_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return SKY_ERR_CUDA;
+  }
+  Engine* e = nullptr;
+  if (kind == SKY_MODEL_PANGU6) {
+    if (cfg_bytes != sizeof(sky_pangu_config_t)) { set_error("bad config size"); return SKY_ERR_ARG; }
+    e = make_pangu_engine(*static_cast<const sky_pangu_config_t*>(cfg), device);
+  } else if (kind == SKY_MODEL_SFNO73) {
+    if (cfg_bytes != sizeof(sky_sfno_config_t)) { set_error("bad config size"); return SKY_ERR_ARG; }
+    e = make_sfno_engine(*static_cast<const sky_sfno_config_t*>(cfg), device);
+  } else {
+    set_error("unknown model kind %d", kind);
+    return SKY_ERR_ARG;
+  }
+  if (!e) return SKY_ERR_ARG;
+  e->num_sms = prop.multiProcessorCount;
+  *out = new sky_model{e};
+  return SKY_OK;
+}
+
+int sky_model_load_weights(sky_model_t* m, const float* arena, uint64_t n_floats, const sky_param_desc_t* manifest,
+                           int32_t n_params, int32_t on_device, void* stream) {
+  if (!m || !arena || !manifest) { set_error("null argument"); return SKY_ERR_ARG; }
+  SKY_CUDA_OK(cudaSetDevice(m->eng->device));
+  return m->eng->load_arena(arena, n_floats, manifest, n_params, on_device, (cudaStream_t)stream);
+}
+
+size_t sky_model_workspace_bytes(const sky_model_t* m, int32_t batch) {
+  return m && batch > 0 ? m->eng->workspace_bytes(batch) : 0;
+}
+
+int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batch, void* ws, size_t ws_bytes,
+                   void* stream) {
+  if (!m || !x_in || !x_out || !ws || batch <= 0) { set_error("bad argument"); return SKY_ERR_ARG; }
+  if (x_in == x_out) { set_error("x_in and x_out may not alias"); return SKY_ERR_ARG; }
+  SKY_CUDA_OK(cudaSetDevice(m->eng->device));
+  return m->eng->step(x_in, x_out, batch, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* ws, int32_t batch,
+                         void* stream) {
+  if (!m || !what || !dst || !ws) { set_error("bad argument"); return SKY_ERR_ARG; }
+  return m->eng->debug_copy(what, dst, max_floats, ws, batch, (cudaStream_t)stream);
+}
+
+int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int32_t member0, int32_t members,
+                   int32_t channels, int64_t plane, void* stream) {
+  if (!x || !sigma_c || members <= 0 || channels <= 0 || plane <= 0) { set_error("bad argument"); return SKY_ERR_ARG; }
+  long long qpp = (plane + 3) / 4;
+  long long total = qpp * channels * members;
+  k_perturb_ic<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, sigma_c, amp, seed, member0,
+                                                                                  channels, plane, qpp, total);
+  count_launch();
+  SKY_CUDA_OK(cudaGetLastError());
+  return SKY_OK;
+}
+
+int sky_model_destroy(sky_model_t* m) {
+  if (!m) return SKY_OK;
+  delete m->eng;
+  delete m;
+  return SKY_OK;
+}
+
+}  // extern "C"

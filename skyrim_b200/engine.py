@@ -1,0 +1,152 @@
+"""Host-side handle on one CUDA step operator (thin Python over the C-ABI).
+
+PyTorch tensors are used as device-memory containers only: the engine receives raw
+``data_ptr()`` addresses and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _ffi
+from .config import PanguConfig, SFNOConfig
+
+ARENA_ALIGN = 64  # floats (256 B)
+
+
+def pack_arena(weights: "OrderedDict[str, np.ndarray]"):
+    """Flatten named fp32 tensors into one arena + manifest (name, offset, count)."""
+    offs, total = [], 0
+    for name, a in weights.items():
+        offs.append(total)
+        total += (a.size + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+    arena = np.zeros(total, dtype=np.float32)
+    manifest = (_ffi.ParamDesc * len(weights))()
+    for i, ((name, a), off) in enumerate(zip(weights.items(), offs)):
+        arena[off:off + a.size] = np.asarray(a, dtype=np.float32).reshape(-1)
+        manifest[i].name = name.encode()
+        manifest[i].offset = off
+        manifest[i].count = a.size
+    return arena, manifest
+
+
+def _pangu_cfg_c(cfg: PanguConfig) -> _ffi.PanguConfigC:
+    assert tuple(cfg.patch) == (2, 4, 4) and tuple(cfg.window) == (2, 6, 12)
+    c = _ffi.PanguConfigC()
+    c.nlat, c.nlon, c.n_levels, c.dim = cfg.nlat, cfg.nlon, cfg.n_levels, cfg.dim
+    c.depths[:] = cfg.depths
+    c.heads[:] = cfg.heads
+    c.ln_eps, c.mask_value = cfg.ln_eps, cfg.mask_value
+    return c
+
+
+def _sfno_cfg_c(cfg: SFNOConfig) -> _ffi.SFNOConfigC:
+    c = _ffi.SFNOConfigC()
+    c.nlat, c.nlon, c.n_channels, c.embed = cfg.nlat, cfg.nlon, cfg.n_channels, cfg.embed
+    c.layers, c.scale_factor, c.mlp_ratio, c.eps = cfg.layers, cfg.scale_factor, cfg.mlp_ratio, cfg.eps
+    return c
+
+
+class StepEngine:
+    """One 6-h step operator resident on one GPU."""
+
+    def __init__(self, cfg, device: int = 0):
+        import torch
+        if not torch.cuda.is_available():
+            raise _ffi.SkyError("skyrim_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = device
+        self.torch = torch
+        L = _ffi.lib()
+        if isinstance(cfg, PanguConfig):
+            kind, cc = _ffi.SKY_MODEL_PANGU6, _pangu_cfg_c(cfg)
+        elif isinstance(cfg, SFNOConfig):
+            kind, cc = _ffi.SKY_MODEL_SFNO73, _sfno_cfg_c(cfg)
+        else:
+            raise TypeError(cfg)
+        self.n_channels = cfg.n_channels
+        h = C.c_void_p()
+        _ffi.check(L.sky_model_create(C.byref(h), kind, C.byref(cc), C.sizeof(cc), device), "sky_model_create")
+        self._h = h
+        self._ws = None
+        self._ws_batch = 0
+
+    # -- weights ---------------------------------------------------------------------------
+    def load_weights(self, weights: "OrderedDict[str, np.ndarray]"):
+        arena, manifest = pack_arena(weights)
+        self.load_arena(arena, manifest)
+
+    def load_arena(self, arena, manifest):
+        """``arena``: host numpy fp32 array, or a CUDA torch tensor (e.g. after a broadcast)."""
+        L = _ffi.lib()
+        torch = self.torch
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        if isinstance(arena, np.ndarray):
+            ptr, n, on_dev = arena.ctypes.data, arena.size, 0
+        else:
+            assert arena.is_cuda and arena.dtype == torch.float32 and arena.is_contiguous()
+            ptr, n, on_dev = arena.data_ptr(), arena.numel(), 1
+        _ffi.check(L.sky_model_load_weights(self._h, ptr, n, manifest, len(manifest), on_dev, st),
+                   "sky_model_load_weights")
+
+    # -- stepping --------------------------------------------------------------------------
+    def _workspace(self, batch: int):
+        if self._ws is None or self._ws_batch < batch:
+            nbytes = _ffi.lib().sky_model_workspace_bytes(self._h, batch)
+            self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=f"cuda:{self.device}")
+            self._ws_batch = batch
+        return self._ws
+
+    def step(self, x_in, x_out=None):
+        """x_in: CUDA fp32 (B, C, nlat, nlon) contiguous.  Returns x_out (allocated if None).
+        Asynchronous on the current stream."""
+        torch = self.torch
+        assert x_in.is_cuda and x_in.dtype == torch.float32 and x_in.is_contiguous() and x_in.dim() == 4
+        B = x_in.shape[0]
+        assert tuple(x_in.shape[1:]) == (self.n_channels, self.cfg.nlat, self.cfg.nlon), x_in.shape
+        if x_out is None:
+            x_out = torch.empty_like(x_in)
+        ws = self._workspace(B)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().sky_model_step(self._h, x_in.data_ptr(), x_out.data_ptr(), B, ws.data_ptr(),
+                                             ws.numel(), st), "sky_model_step")
+        return x_out
+
+    def debug_tensor(self, what: str, shape, batch: int = 1):
+        torch = self.torch
+        out = torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.device}")
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(_ffi.lib().sky_model_debug_copy(self._h, what.encode(), out.data_ptr(), out.numel(),
+                                                   self._workspace(batch).data_ptr(), batch, st), "debug_copy")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().sky_model_destroy(self._h)
+            self._h = None
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def perturb_ic(x, sigma_c, amp: float, seed: int, member0: int = 0):
+    """In-place Gaussian perturbation of (M, C, nlat, nlon) CUDA fp32 members (K11)."""
+    import torch
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    M, Cn = x.shape[0], x.shape[1]
+    plane = x.shape[2] * x.shape[3]
+    assert sigma_c.is_cuda and sigma_c.numel() == Cn
+    st = torch.cuda.current_stream(x.device).cuda_stream
+    _ffi.check(_ffi.lib().sky_perturb_ic(x.data_ptr(), sigma_c.data_ptr(), float(amp), int(seed), int(member0), M,
+                                         Cn, plane, st), "sky_perturb_ic")
+    return x
+
+
+def launch_count() -> int:
+    return int(_ffi.lib().sky_launch_count())
