@@ -97,6 +97,15 @@ int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t 
 int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int32_t member0,
                    int32_t members, int32_t channels, int64_t plane, void* stream);
 
+/* Per-kernel-family device timing (CUDA events recorded on the launching stream around the
+ * launches whose family bit is set in tag_mask).  profile_end synchronises on the recorded
+ * events and returns the summed milliseconds and launch counts per family.  Used by bench.py
+ * for the live roofline figure; off by default (no events are recorded). */
+int sky_model_profile_begin(sky_model_t* m, uint64_t tag_mask);
+int sky_model_profile_end(sky_model_t* m, double* ms_per_tag, uint64_t* launches_per_tag, int32_t n_tags);
+int sky_profile_tag_count(void);
+const char* sky_profile_tag_name(int32_t tag);
+
 /* how many kernels this library has launched since load (bench.py's gpu_launches) */
 uint64_t sky_launch_count(void);
 

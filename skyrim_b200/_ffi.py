@@ -49,6 +49,10 @@ EXPORTS = {
                                        C.c_void_p]),
     "sky_perturb_ic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int64, C.c_void_p]),
+    "sky_model_profile_begin": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sky_model_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int32]),
+    "sky_profile_tag_count": (C.c_int, []),
+    "sky_profile_tag_name": (C.c_char_p, [C.c_int32]),
     "sky_launch_count": (C.c_uint64, []),
     "sky_model_destroy": (C.c_int, [C.c_void_p]),
 }

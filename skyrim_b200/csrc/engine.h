@@ -7,6 +7,7 @@
 #include <atomic>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/skyrim_b200.h"
 
@@ -15,6 +16,11 @@ namespace sky {
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 void set_error(const char* fmt, ...);
+
+// kernel families, used for per-kernel CUDA-event timing (bench.py roofline) and launch counting
+enum KTag { KT_EMBED = 0, KT_QKV, KT_ATTN, KT_PROJ, KT_FC1, KT_FC2, KT_MLP, KT_DOWN, KT_UP, KT_RECOVER, KT_COPY,
+            KT_SFNO_ENC, KT_SFNO_SHT, KT_SFNO_SPEC, KT_SFNO_ISHT, KT_SFNO_MLP, KT_SFNO_DEC, KT_SFNO_MISC, KT_COUNT };
+const char* ktag_name(int tag);
 
 struct ParamView {
   const float* dev;  // device pointer inside the resident fp32 arena
@@ -29,6 +35,20 @@ struct Engine {
   uint64_t arena_floats = 0;
   std::map<std::string, ParamView> params;
   bool loaded = false;
+
+  // optional per-kernel timing: events are recorded around launches whose tag is in prof_mask
+  uint64_t prof_mask = 0;
+  struct ProfRec { cudaEvent_t a, b; int tag; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_event();
+  void prof_begin(int tag, cudaStream_t st) {
+    if (prof_mask >> tag & 1) { ProfRec r{prof_event(), prof_event(), tag}; cudaEventRecord(r.a, st); prof_recs.push_back(r); }
+  }
+  void prof_end(int tag, cudaStream_t st) {
+    if (prof_mask >> tag & 1) cudaEventRecord(prof_recs.back().b, st);
+  }
+  int prof_collect(double* ms, uint64_t* counts, int n);  // synchronises; resets the records
 
   virtual ~Engine();
   int load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,

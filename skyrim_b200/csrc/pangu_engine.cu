@@ -237,14 +237,19 @@ struct PanguEngine : Engine {
 
   // ---- GEMM dispatch -----------------------------------------------------------------------
   template <int BN, class Prod, class Epi>
-  int gemm(const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
+  int gemm(int tag, const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
     if (w.BN != BN) { set_error("internal: weight packed for BLOCK_N=%d used with %d", w.BN, BN); return SKY_ERR_STATE; }
+    int rc;
+    prof_begin(tag, st);
     if (use_ref) {
       count_launch(2);
-      return launch_gemm_ref(prod, epi, w.plain, scratch, M, w.N, w.Kp, BN, st);
+      rc = launch_gemm_ref(prod, epi, w.plain, scratch, M, w.N, w.Kp, BN, st);
+    } else {
+      count_launch();
+      rc = launch_gemm_tc<Prod, Epi, BN>(prod, epi, w.img, M, w.N, w.Kp, num_sms, st);
     }
-    count_launch();
-    return launch_gemm_tc<Prod, Epi, BN>(prod, epi, w.img, M, w.N, w.Kp, num_sms, st);
+    prof_end(tag, st);
+    return rc;
   }
 
   int run_block(float* x, const Geo& g, const BlockW& b, int roll, int B, const Ws& ws, cudaStream_t st) {
@@ -254,30 +259,32 @@ struct PanguEngine : Engine {
     {
       ProdWindow p{x, g, roll, Mw};
       EpiStoreF16<false> e{ws.qkv, 3 * C, b.qkv_b, Mw};
-      if ((rc = gemm<192>(p, e, b.qkv, Mw, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_QKV, p, e, b.qkv, Mw, ws.scratch, st))) return rc;
     }
     {
       dim3 grid(g.heads, (unsigned)(B * g.nWin));
+      prof_begin(KT_ATTN, st);
       k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.att, b.bias_tab, g, roll,
                                                                   rsqrtf(32.f), cfg.mask_value);
+      prof_end(KT_ATTN, st);
       count_launch();
       SKY_CUDA_OK(cudaGetLastError());
     }
     {
       ProdPlainF16 p{ws.att, C, Mw, C};
       EpiLnResidual e{x, C, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps, Mw, 1, g, roll};
-      rc = C == 192 ? gemm<192>(p, e, b.proj, Mw, ws.scratch, st) : gemm<384>(p, e, b.proj, Mw, ws.scratch, st);
+      rc = C == 192 ? gemm<192>(KT_PROJ, p, e, b.proj, Mw, ws.scratch, st) : gemm<384>(KT_PROJ, p, e, b.proj, Mw, ws.scratch, st);
       if (rc) return rc;
     }
     {
       ProdPlainF32 p{x, C, Mt, C};
       EpiStoreF16<true> e{ws.hid, 4 * C, b.fc1_b, Mt};
-      if ((rc = gemm<192>(p, e, b.fc1, Mt, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_FC1, p, e, b.fc1, Mt, ws.scratch, st))) return rc;
     }
     {
       ProdPlainF16 p{ws.hid, 4 * C, Mt, 4 * C};
       EpiLnResidual e{x, C, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps, Mt, 0, g, 0};
-      rc = C == 192 ? gemm<192>(p, e, b.fc2, Mt, ws.scratch, st) : gemm<384>(p, e, b.fc2, Mt, ws.scratch, st);
+      rc = C == 192 ? gemm<192>(KT_FC2, p, e, b.fc2, Mt, ws.scratch, st) : gemm<384>(KT_FC2, p, e, b.fc2, Mt, ws.scratch, st);
       if (rc) return rc;
     }
     return 0;
@@ -299,28 +306,32 @@ struct PanguEngine : Engine {
       long long M = (long long)B * nzt * HW;
       ProdEmbedUpper p{x_in, mean, stdv, cfg.nlat, cfg.nlon, cfg.n_levels, 5, nch, g1.H, g1.W, nzt, M};
       EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW};
-      if ((rc = gemm<192>(p, e, embed_u, M, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_EMBED, p, e, embed_u, M, ws.scratch, st))) return rc;
       long long Ms = (long long)B * HW;
       ProdEmbedSurf ps{x_in, masks, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 4, 3, g1.H, g1.W, Ms};
       EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW};
-      if ((rc = gemm<192>(ps, es, embed_s, Ms, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_EMBED, ps, es, embed_s, Ms, ws.scratch, st))) return rc;
     }
     if (stop == 0) return 0;
     // ---- layer 0 ----
     for (size_t i = 0; i < blocks[0].size(); ++i)
       if ((rc = run_block(ws.x1, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
     if (stop == 1) return 0;
+    prof_begin(KT_COPY, st);
     SKY_CUDA_OK(cudaMemcpyAsync(ws.skip, ws.x1, (size_t)B * g1.T * C * 4, cudaMemcpyDeviceToDevice, st));
+    prof_end(KT_COPY, st);
     // ---- down-sample ----
     {
       long long rows = (long long)B * g2.T;
+      prof_begin(KT_DOWN, st);
       k_down_merge_ln<24><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ws.x1, ws.hid, down_g, down_b, cfg.ln_eps, g1.Z,
                                                                    g1.H, g1.W, C, g2.H, g2.W, rows);
+      prof_end(KT_DOWN, st);
       count_launch();
       SKY_CUDA_OK(cudaGetLastError());
       ProdPlainF16 p{ws.hid, 4 * C, rows, 4 * C};
       EpiStoreF32 e{ws.x2, 2 * C, nullptr, rows, 0, 0, 0, 0};
-      if ((rc = gemm<192>(p, e, down, rows, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_DOWN, p, e, down, rows, ws.scratch, st))) return rc;
     }
     if (stop == 2) return 0;
     for (int li = 1; li <= 2; ++li) {
@@ -333,11 +344,11 @@ struct PanguEngine : Engine {
       long long rows = (long long)B * g2.T;
       ProdPlainF32 p{ws.x2, 2 * C, rows, 2 * C};
       EpiUpShuffleLn e{ws.hid, C, up_g, up_b, cfg.ln_eps, rows, g1.Z, g1.H, g1.W, g2.H, g2.W};
-      if ((rc = gemm<192>(p, e, up1, rows, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_UP, p, e, up1, rows, ws.scratch, st))) return rc;
       long long M = (long long)B * g1.T;
       ProdPlainF16 p2{ws.hid, C, M, C};
       EpiStoreF32 e2{ws.x1, C, nullptr, M, 0, 0, 0, 0};
-      if ((rc = gemm<192>(p2, e2, up2, M, ws.scratch, st))) return rc;
+      if ((rc = gemm<192>(KT_UP, p2, e2, up2, M, ws.scratch, st))) return rc;
     }
     if (stop == 5) return 0;
     for (size_t i = 0; i < blocks[3].size(); ++i)
@@ -348,11 +359,11 @@ struct PanguEngine : Engine {
       long long M = (long long)B * nzt * HW;
       ProdConcat p{ws.skip, ws.x1, C, g1.T, HW, 1, nzt, M};
       EpiRecover e{x_out, rec_u_b, mean, stdv, cfg.nlat, cfg.nlon, nch, 0, cfg.n_levels, 2, g1.H, g1.W, nzt, 160, M};
-      if ((rc = gemm<160>(p, e, rec_u, M, ws.scratch, st))) return rc;
+      if ((rc = gemm<160>(KT_RECOVER, p, e, rec_u, M, ws.scratch, st))) return rc;
       long long Ms = (long long)B * HW;
       ProdConcat ps{ws.skip, ws.x1, C, g1.T, HW, 0, 1, Ms};
       EpiRecover es{x_out, rec_s_b, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 1, 1, g1.H, g1.W, 1, 64, Ms};
-      if ((rc = gemm<64>(ps, es, rec_s, Ms, ws.scratch, st))) return rc;
+      if ((rc = gemm<64>(KT_RECOVER, ps, es, rec_s, Ms, ws.scratch, st))) return rc;
     }
     return 0;
   }

@@ -20,6 +20,34 @@ void set_error(const char* fmt, ...) {
 
 Engine::~Engine() {
   if (arena) cudaFree(arena);
+  for (auto e : prof_pool) cudaEventDestroy(e);
+  for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+}
+
+const char* ktag_name(int t) {
+  static const char* n[KT_COUNT] = {"embed", "qkv", "attn", "proj", "fc1", "fc2", "mlp", "down", "up", "recover", "copy",
+                                    "sfno_enc", "sfno_sht", "sfno_spec", "sfno_isht", "sfno_mlp", "sfno_dec", "sfno_misc"};
+  return t >= 0 && t < KT_COUNT ? n[t] : "?";
+}
+
+cudaEvent_t Engine::prof_event() {
+  if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int Engine::prof_collect(double* ms, uint64_t* counts, int n) {
+  for (int i = 0; i < n; ++i) { ms[i] = 0; counts[i] = 0; }
+  for (auto& r : prof_recs) {
+    SKY_CUDA_OK(cudaEventSynchronize(r.b));
+    float t = 0;
+    SKY_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    if (r.tag < n) { ms[r.tag] += t; counts[r.tag] += 1; }
+    prof_pool.push_back(r.a); prof_pool.push_back(r.b);
+  }
+  prof_recs.clear();
+  return 0;
 }
 
 int Engine::load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,
@@ -182,6 +210,21 @@ int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int
   SKY_CUDA_OK(cudaGetLastError());
   return SKY_OK;
 }
+
+int sky_model_profile_begin(sky_model_t* m, uint64_t tag_mask) {
+  if (!m) { set_error("null model"); return SKY_ERR_ARG; }
+  double ms[KT_COUNT]; uint64_t c[KT_COUNT];
+  m->eng->prof_collect(ms, c, KT_COUNT);
+  m->eng->prof_mask = tag_mask;
+  return SKY_OK;
+}
+int sky_model_profile_end(sky_model_t* m, double* ms_per_tag, uint64_t* launches_per_tag, int32_t n_tags) {
+  if (!m || !ms_per_tag || !launches_per_tag) { set_error("null argument"); return SKY_ERR_ARG; }
+  m->eng->prof_mask = 0;
+  return m->eng->prof_collect(ms_per_tag, launches_per_tag, n_tags);
+}
+int sky_profile_tag_count(void) { return KT_COUNT; }
+const char* sky_profile_tag_name(int32_t tag) { return ktag_name(tag); }
 
 int sky_model_destroy(sky_model_t* m) {
   if (!m) return SKY_OK;

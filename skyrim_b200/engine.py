@@ -122,6 +122,28 @@ class StepEngine:
                                                    self._workspace(batch).data_ptr(), batch, st), "debug_copy")
         return out
 
+    # -- per-kernel-family device timing (CUDA events inside the library) -------------------
+    @staticmethod
+    def profile_tags():
+        L = _ffi.lib()
+        return [L.sky_profile_tag_name(i).decode() for i in range(L.sky_profile_tag_count())]
+
+    def profile_begin(self, tags=None):
+        names = self.profile_tags()
+        mask = 0
+        for i, n in enumerate(names):
+            if tags is None or n in tags:
+                mask |= 1 << i
+        _ffi.check(_ffi.lib().sky_model_profile_begin(self._h, mask), "profile_begin")
+
+    def profile_end(self):
+        """-> {family: (total_ms, launches)} for the families that ran since profile_begin."""
+        names = self.profile_tags()
+        ms = (C.c_double * len(names))()
+        cnt = (C.c_uint64 * len(names))()
+        _ffi.check(_ffi.lib().sky_model_profile_end(self._h, ms, cnt, len(names)), "profile_end")
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names) if cnt[i]}
+
     def close(self):
         if getattr(self, "_h", None):
             _ffi.lib().sky_model_destroy(self._h)

@@ -24,3 +24,12 @@ for i in range(10):
 torch.cuda.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(10)]
 print("B=%d ms/step: %s  -> %.2f member-steps/s" % (B, ["%.2f" % t for t in ts], B * 1000 / np.median(ts)), flush=True)
+# per-family breakdown (events around every launch)
+eng.profile_begin()
+for i in range(3):
+    eng.step(x, y); x, y = y, x
+prof = eng.profile_end()
+tot = sum(v[0] for v in prof.values())
+for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+    print("  %-8s %8.3f ms/step  %3d launches/step  %5.1f%%" % (k, ms / 3, n // 3, 100 * ms / tot), flush=True)
+print("  sum %.2f ms/step" % (tot / 3))

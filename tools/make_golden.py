@@ -1,0 +1,23 @@
+"""Generate the committed golden fixtures under tests/golden/ from the fp64 oracle.
+
+The reference ships no golden vectors for this path ("parity unpinned"), so
+these pin the oracle against itself across refactors: seeded weights + IC -> sampled outputs.
+    python tools/make_golden.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from skyrim_b200.config import pangu_small, PANGU_CHANNELS
+from skyrim_b200.weights import make_pangu_weights, synthetic_state
+from oracle.pangu_ref import PanguRef
+
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+os.makedirs(out, exist_ok=True)
+cfg = pangu_small(41, 96)
+w = make_pangu_weights(cfg, 0)
+x0 = synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0)
+y = PanguRef(cfg, w, torch.float64).step(x0).numpy()
+np.savez_compressed(os.path.join(out, "pangu_41x96_seed0.npz"),
+                    x0_sample=x0[:, ::8, ::16].astype(np.float32), y_sample=y[:, ::5, ::12],
+                    y_norm=np.sqrt((y ** 2).sum(axis=(1, 2))), y_mean=y.mean(axis=(1, 2)))
+print("wrote", os.path.join(out, "pangu_41x96_seed0.npz"))
