@@ -6,14 +6,14 @@
 // Scores, softmax and the accumulators are fp32; the two small GEMMs run on mma.sync
 // m16n8k16 (they are ~6-11 % of the step's FLOPs; the big contractions are tcgen05).
 #pragma once
-#include "pangu_ops.cuh"
+#include "gemm2.cuh"
 
 namespace sky {
 
 constexpr int ATT_THREADS = 96;
 constexpr int ATT_LDS = 40;  // halves per smem row (32 + 8 pad): conflict-free ldmatrix
 constexpr int ATT_TABLE = (2 * WW - 1) * WH * WH * WZ * WZ;  // 3312
-constexpr int ATT_SMEM_BYTES = 3 * WIN_TOK * ATT_LDS * 2 + ATT_TABLE * 4 + WIN_TOK * 4;
+constexpr int ATT_SMEM_BYTES = 3 * WIN_TOK * ATT_LDS * 2 + ATT_TABLE * 4 + 2 * WIN_TOK * 4 + WIN_TOK * 8;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
@@ -33,16 +33,22 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid (heads, total windows); qkv (rows, 3C) fp16 window-ordered; out (rows, C) fp16
+// grid (heads, total windows).  qkv: (tokens, 3C) fp16 in NATURAL token order — the window
+// partition, the cyclic shift and the latitude padding are index arithmetic here and nowhere
+// else; a padding token has x = 0, so its q/k/v are the QKV bias.  Output: fp16 tile image of
+// (tokens, C) (A operand of the projection GEMM), again in natural order.
 __global__ void __launch_bounds__(ATT_THREADS)
-k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
-                   const float* __restrict__ bias_tab, Geo g, int roll, float scale, float mask_value) {
+k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img, int att_nkb,
+                   const float* __restrict__ bias_tab, const float* __restrict__ qkv_bias, Geo g, int roll,
+                   float scale, float mask_value) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* Qs = reinterpret_cast<__half*>(att_smem);
   __half* Ks = Qs + WIN_TOK * ATT_LDS;
   __half* Vs = Ks + WIN_TOK * ATT_LDS;
   float* Bs = reinterpret_cast<float*>(Vs + WIN_TOK * ATT_LDS);
-  int* colinfo = reinterpret_cast<int*>(Bs + ATT_TABLE);  // per key token: table col-part | flags<<24
+  int* colpart = reinterpret_cast<int*>(Bs + ATT_TABLE);  // per key token: column part of the table index (+64)
+  int* colflag = colpart + WIN_TOK;                       // per key token: seam side flags (z: 1, lat: 2)
+  long long* tok = reinterpret_cast<long long*>(colflag + WIN_TOK);
 
   const int head = blockIdx.x;
   const long long wing = blockIdx.y;           // global window index (members stacked)
@@ -52,19 +58,30 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
   const int C = g.C;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
-  // ---- stage Q, K, V (64 B per row each) and the bias table slice ----
-  const __half* src = qkv + wing * WIN_TOK * (3LL * C) + head * 32;
-  for (int i = tid; i < WIN_TOK * 12; i += ATT_THREADS) {
-    int row = i / 12, rem = i % 12, part = rem / 4, ch = rem % 4;
-    cp_async16(Qs + part * WIN_TOK * ATT_LDS + row * ATT_LDS + ch * 8, src + (long long)row * 3 * C + part * C + ch * 8);
+  for (int j = tid; j < WIN_TOK; j += ATT_THREADS) {
+    tok[j] = win_row_to_token(g, roll, wing * WIN_TOK + j);
+    int wj = j % WW, hj = (j / WW) % WH, zj = j / (WW * WH);
+    int part = (WZ * zj) * ((2 * WW - 1) * WH * WH) + (WH * hj) * (2 * WW - 1) - wj;
+    colpart[j] = part + 64;  // +64 keeps it non-negative (the row part carries -64)
+    colflag[j] = (zj >= WZ - SZ ? 1 : 0) | (hj >= WH - SH ? 2 : 0);
   }
   const float* bsrc = bias_tab + ((long long)type * g.heads + head) * ATT_TABLE;
   for (int i = tid; i < ATT_TABLE / 4; i += ATT_THREADS) cp_async16(Bs + 4 * i, bsrc + 4 * i);
-  for (int j = tid; j < WIN_TOK; j += ATT_THREADS) {
-    int wj = j % WW, hj = (j / WW) % WH, zj = j / (WW * WH);
-    int part = (WZ * zj) * ((2 * WW - 1) * WH * WH) + (WH * hj) * (2 * WW - 1) - wj;
-    int flags = (zj >= WZ - SZ ? 1 : 0) | (hj >= WH - SH ? 2 : 0);
-    colinfo[j] = (part + 64) | (flags << 24);  // +64 keeps the packed field non-negative
+  __syncthreads();
+  // ---- stage Q, K, V (64 B per token each) ----
+  for (int i = tid; i < WIN_TOK * 12; i += ATT_THREADS) {
+    int row = i / 12, rem = i % 12, part = rem / 4, ch = rem % 4;
+    __half* dst = Qs + part * WIN_TOK * ATT_LDS + row * ATT_LDS + ch * 8;
+    const long long t = tok[row];
+    if (t >= 0) {
+      cp_async16(dst, qkv + t * 3 * C + part * C + head * 32 + ch * 8);
+    } else {
+      const float* bq = qkv_bias + part * C + head * 32 + ch * 8;
+      uint4 pk;
+      pk.x = pack_half2(bq[0], bq[1]); pk.y = pack_half2(bq[2], bq[3]);
+      pk.z = pack_half2(bq[4], bq[5]); pk.w = pack_half2(bq[6], bq[7]);
+      *reinterpret_cast<uint4*>(dst) = pk;
+    }
   }
   asm volatile("cp.async.commit_group;");
   asm volatile("cp.async.wait_group 0;");
@@ -72,8 +89,9 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
 
   const bool mz = roll && (wzi == g.nWz - 1);
   const bool mh = roll && (whi == g.nWh - 1);
-  const float sl2 = scale * 1.4426950408889634f;  // fold log2(e): softmax via exp2
-  const float l2e = 1.4426950408889634f;
+  const int fmask = (mz ? 1 : 0) | (mh ? 2 : 0);  // CTA-uniform: only seam windows of shifted blocks mask
+  const float sl2 = scale * 1.4426950408889634f;   // scores in log2 units: softmax via exp2
+  const float mask_l2 = mask_value * 1.4426950408889634f;  // (the bias table is pre-scaled by log2 e)
 
   for (int rb = warp; rb < WIN_TOK / 16; rb += ATT_THREADS / 32) {
     const int r0 = rb * 16;
@@ -103,23 +121,30 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
       rowpart[1] = zi * ((2 * WW - 1) * WH * WH) + hi * (2 * WW - 1) + wi + (WW - 1) - 64;
       rflag[1] = (zi >= WZ - SZ ? 1 : 0) | (hi >= WH - SH ? 2 : 0);
     }
-    const int fmask = (mz ? 1 : 0) | (mh ? 2 : 0);
+    const float* B0 = Bs + rowpart[0];
+    const float* B1 = Bs + rowpart[1];
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    if (fmask == 0) {
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
+      for (int nt = 0; nt < 18; ++nt) {
+        const int2 cp2 = *reinterpret_cast<const int2*>(colpart + nt * 8 + 2 * (lane & 3));
+        s[nt][0] = fmaf(s[nt][0], sl2, B0[cp2.x]); s[nt][1] = fmaf(s[nt][1], sl2, B0[cp2.y]);
+        s[nt][2] = fmaf(s[nt][2], sl2, B1[cp2.x]); s[nt][3] = fmaf(s[nt][3], sl2, B1[cp2.y]);
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+      }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int j = nt * 8 + 2 * (lane & 3) + e;
-        int ci = colinfo[j];
-        int cpart = ci & 0xffffff, cflag = ci >> 24;
-        float b0 = Bs[rowpart[0] + cpart], b1 = Bs[rowpart[1] + cpart];
-        float m0 = ((rflag[0] ^ cflag) & fmask) ? mask_value : 0.f;
-        float m1 = ((rflag[1] ^ cflag) & fmask) ? mask_value : 0.f;
-        // work in log2 units
-        float v0 = s[nt][e] * sl2 + (b0 + m0) * l2e;
-        float v1 = s[nt][2 + e] * sl2 + (b1 + m1) * l2e;
-        s[nt][e] = v0; s[nt][2 + e] = v1;
-        mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+      for (int nt = 0; nt < 18; ++nt) {
+        const int j = nt * 8 + 2 * (lane & 3);
+        const int2 cp2 = *reinterpret_cast<const int2*>(colpart + j);
+        const int f0 = colflag[j], f1 = colflag[j + 1];
+        s[nt][0] = fmaf(s[nt][0], sl2, B0[cp2.x]) + (((rflag[0] ^ f0) & fmask) ? mask_l2 : 0.f);
+        s[nt][1] = fmaf(s[nt][1], sl2, B0[cp2.y]) + (((rflag[0] ^ f1) & fmask) ? mask_l2 : 0.f);
+        s[nt][2] = fmaf(s[nt][2], sl2, B1[cp2.x]) + (((rflag[1] ^ f0) & fmask) ? mask_l2 : 0.f);
+        s[nt][3] = fmaf(s[nt][3], sl2, B1[cp2.y]) + (((rflag[1] ^ f1) & fmask) ? mask_l2 : 0.f);
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
@@ -129,8 +154,8 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 18; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] - mx0); s[nt][1] = exp2f(s[nt][1] - mx0);
-      s[nt][2] = exp2f(s[nt][2] - mx1); s[nt][3] = exp2f(s[nt][3] - mx1);
+      s[nt][0] = mufu_ex2(s[nt][0] - mx0); s[nt][1] = mufu_ex2(s[nt][1] - mx0);
+      s[nt][2] = mufu_ex2(s[nt][2] - mx1); s[nt][3] = mufu_ex2(s[nt][3] - mx1);
       sum0 += s[nt][0] + s[nt][1];
       sum1 += s[nt][2] + s[nt][3];
     }
@@ -140,17 +165,19 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
 
-    // O = P V : k runs over the 144 keys in 9 steps of 16
+    // O = P V : k runs over the 144 keys in 9 steps of 16.  P = exp2(s - max) in (0, 1] goes to
+    // the tensor cores un-normalised; the 1/sum is applied to the 16x32 output instead of the
+    // 16x144 probabilities.
     float o[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 9; ++kk) {
       uint32_t pa[4];
-      pa[0] = pack_half2(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-      pa[1] = pack_half2(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-      pa[2] = pack_half2(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-      pa[3] = pack_half2(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+      pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
         uint32_t vb[4];
@@ -159,12 +186,14 @@ k_window_attention(const __half* __restrict__ qkv, __half* __restrict__ out,
         mma16816(o[2 * np + 1], pa, vb[2], vb[3]);
       }
     }
-    __half* orow0 = out + (wing * WIN_TOK + i0) * (long long)C + head * 32 + 2 * (lane & 3);
-    __half* orow1 = orow0 + 8LL * C;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= inv0; o[nt][1] *= inv0; o[nt][2] *= inv1; o[nt][3] *= inv1; }
+    const long long t0 = tok[i0], t1 = tok[i1];
+    const int colb = head * 32 + 2 * (lane & 3);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      *reinterpret_cast<uint32_t*>(orow0 + nt * 8) = pack_half2(o[nt][0], o[nt][1]);
-      *reinterpret_cast<uint32_t*>(orow1 + nt * 8) = pack_half2(o[nt][2], o[nt][3]);
+      if (t0 >= 0) *reinterpret_cast<uint32_t*>(att_img + img_offset(t0, colb + nt * 8, att_nkb)) = pack_half2(o[nt][0], o[nt][1]);
+      if (t1 >= 0) *reinterpret_cast<uint32_t*>(att_img + img_offset(t1, colb + nt * 8, att_nkb)) = pack_half2(o[nt][2], o[nt][3]);
     }
   }
 }

@@ -1,0 +1,458 @@
+// TMA-fed persistent tcgen05 GEMM (v2 data flow):
+//
+//   D[M, N] = A[M, K] * W[N, K]^T -> fused epilogue
+//
+// Both operands arrive as pre-built SWIZZLE_128B "tile images" and are fetched by ONE thread
+// with 1-D bulk copies through the TMA engine (cp.async.bulk + mbarrier complete_tx):
+//   A image  [ceil(M/128)][K/64][128 rows x 128 B]   fp16 activations, written in this layout
+//                                                     by the epilogue of the producing kernel
+//   W image  [N/BLOCK_N][K/64][BLOCK_N rows x 128 B]  packed once at weight load
+// so no warp ever touches the operands with ld/st.  Warp roles: 0..EPI_WARPS-1 epilogue
+// (warp%4 selects the TMEM lane quarter, warp/4 the column partition), then one loader warp
+// and one MMA warp.  Epilogues re-tile their 32x32 accumulator blocks through a padded smem
+// patch so that every global access is a full 64/128-byte row segment (the v1 row-per-lane
+// epilogue was L1-wavefront and latency bound: profiles/r1_gemm_v1.md).
+#pragma once
+#include "pangu_ops.cuh"
+
+namespace sky {
+
+constexpr int G2_BLOCK_M = 128;
+constexpr int G2_A_BYTES = G2_BLOCK_M * 128;
+constexpr int G2_PATCH_LD = 33;
+constexpr int G2_PATCH_FLOATS = 32 * G2_PATCH_LD;
+
+// element (row, col) of an fp16 tile image with nkb k-blocks per row tile -> byte offset
+__device__ __forceinline__ size_t img_offset(long long row, int col, int nkb) {
+  long long tile = row >> 7;
+  uint32_t r = (uint32_t)(row & 127);
+  return ((size_t)tile * nkb + (col >> 6)) * (size_t)G2_A_BYTES + sw128_offset(r, (col & 63) >> 3) + (col & 7) * 2;
+}
+
+// A operand made of one or two images concatenated along K (patch recovery reads
+// concat(skip, x) without materialising it)
+struct AImage {
+  const uint8_t* img0; const uint8_t* img1;
+  int nkb0, nkb1;  // k-blocks per row tile in each image
+  __device__ const uint8_t* kblock(int mt, int kb) const {
+    return kb < nkb0 ? img0 + ((size_t)mt * nkb0 + kb) * G2_A_BYTES
+                     : img1 + ((size_t)mt * nkb1 + (kb - nkb0)) * G2_A_BYTES;
+  }
+};
+
+template <int BLOCK_N, int EPI_WARPS>
+struct G2Cfg {
+  static constexpr int N_INST = BLOCK_N <= 256 ? BLOCK_N : BLOCK_N / 2;
+  static constexpr int N_SPLIT = BLOCK_N / N_INST;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = G2_A_BYTES + B_BYTES;
+  static constexpr int PATCH_BYTES = EPI_WARPS * G2_PATCH_FLOATS * 4;
+  static constexpr int VEC_BYTES = 512 * 4;  // smem copy of the bias (LN epilogues), <= 512 floats
+  static constexpr int FIXED = 1024 /*align*/ + 256 /*barriers*/ + PATCH_BYTES + VEC_BYTES;
+  static constexpr int MAXS = (232448 - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = MAXS > 6 ? 6 : MAXS;
+  static constexpr int NBUF = 2 * BLOCK_N <= 512 ? 2 : 1;
+  static constexpr int COLS = NBUF * BLOCK_N;
+  static constexpr int TMEM_COLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+  static constexpr int THREADS = (EPI_WARPS + 2) * 32;
+  static_assert(N_INST % 16 == 0 && N_INST <= 256, "UMMA shape");
+  static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
+  static_assert(STAGES >= 2, "pipeline depth");
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
+};
+
+struct EpiCtx {
+  long long row0;   // first row of this warp's 32-row group
+  long long M;
+  int lane;
+  int n0;           // first column of the tile in the full N
+  int part, nparts; // column-chunk partition among the warps sharing a lane quarter
+  float* patch;     // [32][33] floats, private to the warp
+  const float* sbias;  // smem copy of bias[0..BLOCK_N) (valid when the epilogue asked for it)
+};
+
+struct AccTmem2 {
+  uint32_t taddr;
+  __device__ void load32(int c, float (&v)[32]) const { tmem_ld32(taddr + (uint32_t)c, v); }
+};
+
+template <class Epi, int BLOCK_N, int EPI_WARPS>
+__global__ void __launch_bounds__((EPI_WARPS + 2) * 32, 1)
+k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long long M, int num_kb,
+        int num_m_tiles, int num_n_tiles) {
+  using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* patches = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  float* sbias = patches + EPI_WARPS * G2_PATCH_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 512);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  constexpr int LOADER = EPI_WARPS, MMAW = EPI_WARPS + 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (Epi::kNeedsBias && threadIdx.x < EPI_WARPS * 32)
+    for (int i = threadIdx.x; i < BLOCK_N; i += EPI_WARPS * 32) sbias[i] = epi.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == LOADER) {
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / num_n_tiles, nt = tile % num_n_tiles;
+      const uint8_t* wsrc = Wimg + (size_t)nt * num_kb * Cfg::B_BYTES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (lane == 0) {
+          uint8_t* dst = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          bulk_g2s(dst, A.kblock(mt, kb), G2_A_BYTES, &full[s]);
+          bulk_g2s(dst + G2_A_BYTES, wsrc + (size_t)kb * Cfg::B_BYTES, Cfg::B_BYTES, &full[s]);
+        }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == MMAW) {
+    constexpr uint32_t idesc = make_idesc_f16(G2_BLOCK_M, Cfg::N_INST);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % Cfg::NBUF;
+      const uint32_t use = (uint32_t)(it / Cfg::NBUF);
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc_sw128(a_addr + k * 32);
+#pragma unroll
+            for (int ni = 0; ni < Cfg::N_SPLIT; ++ni) {
+              const uint64_t db = make_desc_sw128(b_addr + ni * Cfg::N_INST * 128 + k * 32);
+              tc_mma_f16(d_tmem + ni * Cfg::N_INST, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[s]);
+          if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    const int q = warp & 3, part = warp >> 2;
+    EpiCtx ctx;
+    ctx.M = M; ctx.lane = lane; ctx.part = part; ctx.nparts = EPI_WARPS / 4;
+    ctx.patch = patches + warp * G2_PATCH_FLOATS;
+    ctx.sbias = sbias;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % Cfg::NBUF;
+      const uint32_t use = (uint32_t)(it / Cfg::NBUF);
+      ctx.row0 = (long long)(tile / num_n_tiles) * G2_BLOCK_M + q * 32;
+      ctx.n0 = (tile % num_n_tiles) * BLOCK_N;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N)};
+      epi.template run<BLOCK_N>(acc, ctx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == MMAW) {
+    __syncwarp();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <class Epi, int BLOCK_N, int EPI_WARPS>
+int launch_gemm2(const AImage& A, const Epi& epi, const uint8_t* Wimg, long long M, int N, int Kp, int num_sms,
+                 cudaStream_t st) {
+  using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
+  auto kern = k_gemm2<Epi, BLOCK_N, EPI_WARPS>;
+  static bool configured = false;
+  if (!configured) {
+    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_m_tiles = (int)((M + G2_BLOCK_M - 1) / G2_BLOCK_M);
+  const int num_n_tiles = N / BLOCK_N;
+  const int tiles = num_m_tiles * num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, epi, Wimg, M, Kp / 64, num_m_tiles, num_n_tiles);
+  SKY_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ======================================================================================
+// v2 epilogues.  acc.load32(c, v): this lane's row (ctx.row0 + lane), columns [c, c+32).
+// The 32x32 block is re-tiled through ctx.patch so global accesses run along rows.
+// ======================================================================================
+__device__ __forceinline__ void patch_put(float* patch, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) patch[lane * G2_PATCH_LD + j] = v[j];
+}
+
+// fp16 output, optional GELU: row-major [M, ldo] (kImage = false) or tile image with nkb
+// k-blocks per row tile (kImage = true).
+template <bool kGelu, bool kImage>
+struct Epi2F16 {
+  static constexpr bool kNeedsBias = false;
+  __half* out; int ldo; int nkb; const float* bias;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtx& x) const {
+    const int cp = 2 * (x.lane & 15), hr = x.lane >> 4;
+    for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
+      float v[32];
+      acc.load32(c, v);
+      // bias + activation in the row domain: 32 independent dependency chains per thread
+      // (doing it after the re-tiling left 2 chains per thread and was latency bound)
+      const float4* bp = reinterpret_cast<const float4*>(bias + x.n0 + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+      if (kGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      patch_put(x.patch, x.lane, v);
+      __syncwarp();
+      const int col = x.n0 + c + cp;
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        const int rr = 2 * it + hr;
+        const float y0 = x.patch[rr * G2_PATCH_LD + cp], y1 = x.patch[rr * G2_PATCH_LD + cp + 1];
+        const long long row = x.row0 + rr;
+        if (row < x.M) {
+          uint32_t pk = pack_half2(y0, y1);
+          if (kImage) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(out) + img_offset(row, col, nkb)) = pk;
+          else *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pk;
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
+// xf32[row, n0+col] (=|+=) f(acc)  and the fp16 tile image of the new rows.
+//   kLn:       y = LayerNorm(acc + bias) * gamma + beta  (tile spans the feature width: n0 == 0)
+//   kResidual: x += y, else x = y  (bias, if any, is applied when !kLn as well)
+template <bool kLn, bool kResidual>
+struct Epi2F32Img {
+  static constexpr bool kNeedsBias = kLn;
+  float* x; int ldx;            // fp32 row-major
+  uint8_t* img; int nkb;        // fp16 image of the same rows (may be null)
+  const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtx& e) const {
+    // the residual rows are prefetched one column chunk ahead (the first chunk before the
+    // statistics pass): the epilogue is bound by the latency of these loads, not by bandwidth
+    float xin[32];
+    if (kResidual) {
+      const int col0 = e.n0 + e.part * 32 + e.lane;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long row = e.row0 + rr;
+        xin[rr] = (row < e.M && e.part * 32 < BN) ? x[row * ldx + col0] : 0.f;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (kLn) {
+      float s = 0.f, ss = 0.f;
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        acc.load32(c, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b = *reinterpret_cast<const float4*>(e.sbias + c + j);
+          float y0 = v[j] + b.x, y1 = v[j + 1] + b.y, y2 = v[j + 2] + b.z, y3 = v[j + 3] + b.w;
+          s += (y0 + y1) + (y2 + y3);
+          ss += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+        }
+      }
+      mean = s / BN;
+      rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+    }
+    const int cp = 2 * (e.lane & 15), hr = e.lane >> 4;
+    const int step = 32 * e.nparts;
+    for (int c = e.part * 32; c < BN; c += step) {
+      float v[32];
+      acc.load32(c, v);
+      if (kLn) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (v[j] + e.sbias[c + j] - mean) * rstd;
+      }
+      patch_put(e.patch, e.lane, v);
+      __syncwarp();
+      const int col = e.n0 + c + e.lane;
+      float g = 1.f, b = 0.f;
+      if (kLn) { g = __ldg(gamma + col); b = __ldg(beta + col); }
+      else if (bias) b = __ldg(bias + col);
+      float xnext[32];
+      if (kResidual) {
+        const bool more = c + step < BN;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long row = e.row0 + rr;
+          xnext[rr] = (more && row < e.M) ? x[row * ldx + col + step] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long row = e.row0 + rr;
+        float y = e.patch[rr * G2_PATCH_LD + e.lane] * g + b;
+        if (kResidual) y += xin[rr];
+        if (row < e.M) x[row * ldx + col] = y;
+        e.patch[rr * G2_PATCH_LD + e.lane] = y;
+      }
+      __syncwarp();
+      if (img) {
+        const int colp = e.n0 + c + cp;
+#pragma unroll 8
+        for (int it = 0; it < 16; ++it) {
+          const int rr = 2 * it + hr;
+          const long long row = e.row0 + rr;
+          if (row < e.M)
+            *reinterpret_cast<uint32_t*>(img + img_offset(row, colp, nkb)) =
+                pack_half2(e.patch[rr * G2_PATCH_LD + cp], e.patch[rr * G2_PATCH_LD + cp + 1]);
+        }
+      }
+      __syncwarp();
+      if (kResidual) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) xin[rr] = xnext[rr];
+      }
+    }
+  }
+};
+
+// up-sample linear1 (N = 4C as (hs, ws, C); one n-tile = one sub-position): LayerNorm over
+// the C features of the tile, written as fp16 image rows of the FINE token
+// (z, 2*h2+hs, 2*w2+ws) when it survives the crop.
+struct Epi2UpShuffle {
+  static constexpr bool kNeedsBias = false;
+  uint8_t* img; int nkb; int C; const float* gamma; const float* beta; float eps; const float* bias;  // bias unused
+  int H, W, H2, W2;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtx& e) const {
+    float s = 0.f, ss = 0.f;
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      acc.load32(c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s += v[j]; ss += v[j] * v[j]; }
+    }
+    const float mean = s / BN, rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+    const int sub = e.n0 / C, hs = sub >> 1, ws = sub & 1;
+    long long dst = -1;
+    {
+      const long long row = e.row0 + e.lane;
+      if (row < e.M) {
+        int w2 = (int)(row % W2); long long qq = row / W2;
+        int h2 = (int)(qq % H2); qq /= H2;  // member*Z + z
+        int h = 2 * h2 + hs, w = 2 * w2 + ws;
+        if (h < H) dst = (qq * H + h) * W + w;
+      }
+    }
+    const int cp = 2 * (e.lane & 15), hr = e.lane >> 4;
+    for (int c = e.part * 32; c < BN; c += 32 * e.nparts) {
+      float v[32];
+      acc.load32(c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd;
+      patch_put(e.patch, e.lane, v);
+      __syncwarp();
+      const float g0 = __ldg(gamma + c + cp), g1 = __ldg(gamma + c + cp + 1);
+      const float b0 = __ldg(beta + c + cp), b1 = __ldg(beta + c + cp + 1);
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        const int rr = 2 * it + hr;
+        const long long d = __shfl_sync(0xffffffffu, dst, rr);
+        if (d >= 0)
+          *reinterpret_cast<uint32_t*>(img + img_offset(d, c + cp, nkb)) =
+              pack_half2(e.patch[rr * G2_PATCH_LD + cp] * g0 + b0, e.patch[rr * G2_PATCH_LD + cp + 1] * g1 + b1);
+      }
+      __syncwarp();
+    }
+  }
+};
+
+// patch recovery over ALL tokens with N = 160 (upper, cols ((v*2+dz)*4+dh)*4+dw) + 64
+// (surface, cols 160 + (v*4+dh)*4+dw): a token of slab z == 0 takes the surface columns, the
+// others the upper-air ones.  Consecutive lanes are consecutive longitudes, so the float4
+// stores of a warp already form contiguous 512-byte runs: no re-tiling needed.
+struct Epi2Recover {
+  static constexpr bool kNeedsBias = false;
+  float* out; const float* bias /*[5+4]*/; const float* mean; const float* stdv;
+  int nlat, nlon, nch, nup, nlev, H, W, T;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtx& e) const {
+    const long long row = e.row0 + e.lane;
+    const bool ok = row < e.M;
+    long long b = 0; int z = 0, h = 0, w = 0;
+    if (ok) {
+      int t = (int)(row % T); b = row / T;
+      w = t % W; int q2 = t / W; h = q2 % H; z = q2 / H;
+    }
+    for (int c = e.part * 32; c < BN; c += 32 * e.nparts) {
+      float v[32];
+      acc.load32(c, v);
+      if (!ok) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = c + 4 * j;
+        int ch, lat, vv;
+        if (col < 160) {
+          if (z == 0) continue;
+          int dh = (col >> 2) & 3, dz = (col >> 4) & 1;
+          vv = col >> 5;
+          int lev = 2 * (z - 1) + dz;
+          lat = 4 * h + dh;
+          if (lev >= nlev) continue;
+          ch = vv * nlev + lev;
+        } else {
+          if (z != 0) continue;
+          int cs = col - 160;
+          int dh = (cs >> 2) & 3;
+          vv = 5 + (cs >> 4);
+          lat = 4 * h + dh;
+          ch = nup + (cs >> 4);
+        }
+        if (lat >= nlat) continue;
+        const float bsv = __ldg(bias + vv), mu = __ldg(mean + ch), sd = __ldg(stdv + ch);
+        float4 t4;
+        t4.x = (v[4 * j + 0] + bsv) * sd + mu; t4.y = (v[4 * j + 1] + bsv) * sd + mu;
+        t4.z = (v[4 * j + 2] + bsv) * sd + mu; t4.w = (v[4 * j + 3] + bsv) * sd + mu;
+        *reinterpret_cast<float4*>(out + ((b * nch + ch) * (long long)nlat + lat) * nlon + 4 * w) = t4;
+      }
+    }
+  }
+};
+
+}  // namespace sky

@@ -1,6 +1,12 @@
 // Pangu-Weather 6-h step operator on sm_100a: weight repacking + the per-step kernel
 // sequence.  Replaces what /root/reference/skyrim/core/models/pangu.py:45-46 loads
 // (two ONNXRuntime sessions) and what utils.py:34 steps.
+//
+// Data flow (v2): every token matrix lives in NATURAL token order (member, z, lat, lon).
+//   x   fp32 row-major (rows, C)                  the residual stream
+//   xh  fp16 "tile image" [rows/128][C/64][128x128B SWIZZLE_128B]   = the A operand of the next
+//       GEMM, written by the epilogue that produced x and fetched by 1-D bulk copies
+// Windowing / cyclic shift / padding exist only as index arithmetic inside the attention kernel.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -8,6 +14,8 @@
 
 #include "attention.cuh"
 #include "engine.h"
+#include "gemm2.cuh"
+#include "gemm2_ref.cuh"
 #include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
 
@@ -16,30 +24,33 @@ namespace sky {
 // ======================================================================================
 // weight repacking (runs once, at load)
 // ======================================================================================
-// fp32 W (logical [N, K]; stored [N,K] or, if transposed, [K,N]) ->
-//   plain fp16 [N, Kp]  and  tile image [N/BN][Kp/64][BN rows x 128 B, SWIZZLE_128B]
-__global__ void k_pack_weight(const float* __restrict__ W, int N, int K, int Kp, int BN, int transposed,
-                              __half* __restrict__ plain, uint8_t* __restrict__ img) {
+// fp32 W (logical [Nsrc, K]; stored [Nsrc,K] or, if transposed, [K,Nsrc]) -> rows
+// [n_off, n_off+Nsrc) of   plain fp16 [Ntot, Kp]   and   tile image
+// [Ntot/BN][Kp/64][BN rows x 128 B, SWIZZLE_128B]
+__global__ void k_pack_weight(const float* __restrict__ W, int Nsrc, int K, int Kp, int BN, int transposed,
+                              int n_off, __half* __restrict__ plain, uint8_t* __restrict__ img) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one 8-half chunk each
   int chunks_per_row = Kp / 8;
-  if (idx >= (long long)N * chunks_per_row) return;
-  int n = (int)(idx / chunks_per_row), kc = (int)(idx % chunks_per_row);
+  if (idx >= (long long)Nsrc * chunks_per_row) return;
+  int ns = (int)(idx / chunks_per_row), kc = (int)(idx % chunks_per_row);
   __half h[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     int k = kc * 8 + e;
     float v = 0.f;
-    if (k < K) v = transposed ? W[(long long)k * N + n] : W[(long long)n * K + k];
+    if (k < K) v = transposed ? W[(long long)k * Nsrc + ns] : W[(long long)ns * K + k];
     h[e] = __float2half_rn(v);
   }
   uint4 pk = *reinterpret_cast<uint4*>(h);
+  const int n = n_off + ns;
   *reinterpret_cast<uint4*>(plain + (long long)n * Kp + kc * 8) = pk;
   int nt = n / BN, nr = n % BN, kb = kc / 8, ch = kc % 8;
   size_t tile = ((size_t)nt * (Kp / 64) + kb) * (size_t)BN * 128;
   *reinterpret_cast<uint4*>(img + tile + sw128_offset(nr, ch)) = pk;
 }
 
-// earth-specific bias (3312, n_type, heads) -> (n_type, heads, 3312)
+// earth-specific bias (3312, n_type, heads) -> (n_type, heads, 3312), pre-scaled by log2(e)
+// (the attention kernel computes its softmax with exp2)
 __global__ void k_pack_bias_table(const float* __restrict__ src, float* __restrict__ dst, int L, int n_type,
                                   int heads) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,16 +58,16 @@ __global__ void k_pack_bias_table(const float* __restrict__ src, float* __restri
   if (idx >= tot) return;
   int l = (int)(idx % L);
   long long th = idx / L;  // type*heads + head
-  dst[idx] = src[(long long)l * n_type * heads + th];
+  dst[idx] = src[(long long)l * n_type * heads + th] * 1.4426950408889634f;
 }
 
-// DownSample front end: 2x2 (lat, lon) merge + zero pad + LayerNorm(4C) -> fp16 rows.
+// DownSample front end: 2x2 (lat, lon) merge + zero pad + LayerNorm(4C) -> fp16 tile image.
 // One warp per output row; NPL = (4C)/32 values per lane.
 template <int NPL>
-__global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__ x, __half* __restrict__ out,
+__global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__ x, uint8_t* __restrict__ img,
                                                        const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int Z, int H,
-                                                       int W, int C, int H2, int W2, long long rows) {
+                                                       const float* __restrict__ beta, float eps, int H, int W,
+                                                       int C, int H2, int W2, long long rows) {
   long long row = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   int lane = threadIdx.x % 32;
   if (row >= rows) return;
@@ -80,8 +91,18 @@ __global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     int e = lane + 32 * i;
-    out[row * (NPL * 32) + e] = __float2half_rn((v[i] - mean) * rstd * gamma[e] + beta[e]);
+    *reinterpret_cast<__half*>(img + img_offset(row, e, NPL / 2)) =
+        __float2half_rn((v[i] - mean) * rstd * gamma[e] + beta[e]);
   }
+}
+
+// test tap: fp16 image -> fp32 row-major
+__global__ void k_image_to_rows(const uint8_t* __restrict__ img, int nkb, float* __restrict__ out, long long rows,
+                                int cols) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  long long r = idx / cols; int c = (int)(idx % cols);
+  out[idx] = __half2float(*reinterpret_cast<const __half*>(img + img_offset(r, c, nkb)));
 }
 
 // ======================================================================================
@@ -104,9 +125,10 @@ struct PanguEngine : Engine {
   int nch, nup;
   bool use_ref = false;
   std::vector<void*> owned;
-  GemmW embed_u, embed_s, down, up1, up2, rec_u, rec_s;
+  GemmW embed_u, embed_s, down, up1, up2, rec;
   std::vector<BlockW> blocks[4];
-  const float *mean, *stdv, *masks, *embed_u_b, *embed_s_b, *down_g, *down_b, *up_g, *up_b, *rec_u_b, *rec_s_b;
+  const float *mean, *stdv, *masks, *embed_u_b, *embed_s_b, *down_g, *down_b, *up_g, *up_b;
+  float* rec_b = nullptr;  // 5 upper + 4 surface
 
   PanguEngine(const sky_pangu_config_t& c, int dev) : cfg(c) {
     device = dev;
@@ -139,19 +161,26 @@ struct PanguEngine : Engine {
     return reinterpret_cast<T*>(p);
   }
 
-  int pack(GemmW& g, const char* name, int N, int K, int BN, bool transposed, cudaStream_t st) {
-    const float* w = param(name, (uint64_t)N * K);
-    if (!w) return SKY_ERR_ARG;
+  int pack_alloc(GemmW& g, int N, int K, int BN) {
     g.N = N; g.K = K; g.Kp = (K + 63) / 64 * 64; g.BN = BN;
-    if (N % BN) { set_error("%s: N=%d not a multiple of BLOCK_N=%d", name, N, BN); return SKY_ERR_ARG; }
+    if (N % BN) { set_error("N=%d not a multiple of BLOCK_N=%d", N, BN); return SKY_ERR_ARG; }
     g.plain = dalloc<__half>((size_t)N * g.Kp);
     g.img = dalloc<uint8_t>((size_t)N * g.Kp * 2);
-    if (!g.plain || !g.img) return SKY_ERR_NOMEM;
-    long long chunks = (long long)N * g.Kp / 8;
-    k_pack_weight<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(w, N, K, g.Kp, BN, transposed ? 1 : 0, g.plain, g.img);
+    return (g.plain && g.img) ? 0 : SKY_ERR_NOMEM;
+  }
+  int pack_rows(GemmW& g, const char* name, int Nsrc, int n_off, bool transposed, cudaStream_t st) {
+    const float* w = param(name, (uint64_t)Nsrc * g.K);
+    if (!w) return SKY_ERR_ARG;
+    long long chunks = (long long)Nsrc * g.Kp / 8;
+    k_pack_weight<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(w, Nsrc, g.K, g.Kp, g.BN, transposed ? 1 : 0, n_off,
+                                                                 g.plain, g.img);
     count_launch();
     SKY_CUDA_OK(cudaGetLastError());
     return 0;
+  }
+  int pack(GemmW& g, const char* name, int N, int K, int BN, bool transposed, cudaStream_t st) {
+    int rc = pack_alloc(g, N, K, BN);
+    return rc ? rc : pack_rows(g, name, N, 0, transposed, st);
   }
 
   int prepare(cudaStream_t st) override {
@@ -162,15 +191,22 @@ struct PanguEngine : Engine {
     P(embed_u_b, "embed.upper.b", C); P(embed_s_b, "embed.surf.b", C);
     P(down_g, "down.ln.g", 4 * C); P(down_b, "down.ln.b", 4 * C);
     P(up_g, "up.ln.g", C); P(up_b, "up.ln.b", C);
-    P(rec_u_b, "recover.upper.b", 5); P(rec_s_b, "recover.surf.b", 4);
+    const float *ru, *rs;
+    P(ru, "recover.upper.b", 5); P(rs, "recover.surf.b", 4);
+    rec_b = dalloc<float>(16);
+    if (!rec_b) return SKY_ERR_NOMEM;
+    SKY_CUDA_OK(cudaMemcpyAsync(rec_b, ru, 5 * 4, cudaMemcpyDeviceToDevice, st));
+    SKY_CUDA_OK(cudaMemcpyAsync(rec_b + 5, rs, 4 * 4, cudaMemcpyDeviceToDevice, st));
     int rc;
     if ((rc = pack(embed_u, "embed.upper.w", C, 160, 192, false, st))) return rc;
     if ((rc = pack(embed_s, "embed.surf.w", C, 112, 192, false, st))) return rc;
     if ((rc = pack(down, "down.w", 2 * C, 4 * C, 192, false, st))) return rc;
     if ((rc = pack(up1, "up.w1", 4 * C, 2 * C, 192, false, st))) return rc;
     if ((rc = pack(up2, "up.w2", C, C, 192, false, st))) return rc;
-    if ((rc = pack(rec_u, "recover.upper.w", 160, 2 * C, 160, true, st))) return rc;
-    if ((rc = pack(rec_s, "recover.surf.w", 64, 2 * C, 64, true, st))) return rc;
+    // patch recovery: one N = 160 + 64 weight (upper-air | surface columns)
+    if ((rc = pack_alloc(rec, 224, 2 * C, 224))) return rc;
+    if ((rc = pack_rows(rec, "recover.upper.w", 160, 0, true, st))) return rc;
+    if ((rc = pack_rows(rec, "recover.surf.w", 64, 160, true, st))) return rc;
     for (int li = 0; li < 4; ++li) {
       const Geo& g = (li == 0 || li == 3) ? g1 : g2;
       const int c = g.C, heads = cfg.heads[li], n_type = g.nWz * g.nWh;
@@ -205,30 +241,34 @@ struct PanguEngine : Engine {
 
   // ---- workspace carving -----------------------------------------------------------------
   struct Ws {
-    float *x1, *skip, *x2, *scratch;
-    __half *qkv, *att, *hid;
+    float *x1, *x2, *scratch;
+    uint8_t *x1h, *skiph, *x2h, *atth, *hidh;
+    __half* qkv;
+    size_t x1h_bytes;
     size_t total;
   };
+  static size_t tiles(long long rows) { return (size_t)((rows + 127) / 128); }
   Ws carve(void* base, int B) const {
     Ws w;
     size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return (char*)base + o; };
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return (char*)base + o; };
     const size_t C = cfg.dim;
-    size_t rows_win1 = (size_t)B * g1.nWin * WIN_TOK, rows_win2 = (size_t)B * g2.nWin * WIN_TOK;
-    size_t qkv_el = rows_win1 * 3 * C > rows_win2 * 6 * C ? rows_win1 * 3 * C : rows_win2 * 6 * C;
-    size_t hid_el = (size_t)B * g1.T * 4 * C;  // >= B*T2*8C, B*T2*4C (down), B*T1*C (up)
-    w.x1 = (float*)take((size_t)B * g1.T * C * 4);
-    w.skip = (float*)take((size_t)B * g1.T * C * 4);
-    w.x2 = (float*)take((size_t)B * g2.T * 2 * C * 4);
+    const long long R1 = (long long)B * g1.T, R2 = (long long)B * g2.T;
+    const size_t t1 = tiles(R1), t2 = tiles(R2);
+    w.x1 = (float*)take((size_t)R1 * C * 4);
+    w.x2 = (float*)take((size_t)R2 * 2 * C * 4);
+    w.x1h_bytes = t1 * (C / 64) * G2_A_BYTES;
+    w.x1h = (uint8_t*)take(w.x1h_bytes);
+    w.skiph = (uint8_t*)take(w.x1h_bytes);
+    w.x2h = (uint8_t*)take(t2 * (2 * C / 64) * G2_A_BYTES);
+    size_t qkv_el = (size_t)R1 * 3 * C > (size_t)R2 * 6 * C ? (size_t)R1 * 3 * C : (size_t)R2 * 6 * C;
     w.qkv = (__half*)take(qkv_el * 2);
-    w.att = (__half*)take(qkv_el / 3 * 2);
-    w.hid = (__half*)take(hid_el * 2);
+    size_t att_b = t1 * (C / 64) > t2 * (2 * C / 64) ? t1 * (C / 64) : t2 * (2 * C / 64);
+    w.atth = (uint8_t*)take(att_b * G2_A_BYTES);
+    size_t hid_b = t1 * (4 * C / 64) > t2 * (8 * C / 64) ? t1 * (4 * C / 64) : t2 * (8 * C / 64);
+    w.hidh = (uint8_t*)take(hid_b * G2_A_BYTES);  // MLP hidden; also the down-sample / up-sample staging images
     size_t scr = 0;
-    if (use_ref) {
-      scr = rows_win1 * 3 * C;
-      if (hid_el > scr) scr = hid_el;
-      scr *= 4;
-    }
+    if (use_ref) scr = (size_t)R1 * 4 * C * 4;
     w.scratch = (float*)take(scr);
     w.total = off;
     return w;
@@ -236,9 +276,24 @@ struct PanguEngine : Engine {
   size_t workspace_bytes(int batch) const override { return carve(nullptr, batch).total; }
 
   // ---- GEMM dispatch -----------------------------------------------------------------------
-  template <int BN, class Prod, class Epi>
-  int gemm(int tag, const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
+  template <int BN, int EW, class Epi>
+  int gemm2(int tag, const AImage& A, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
     if (w.BN != BN) { set_error("internal: weight packed for BLOCK_N=%d used with %d", w.BN, BN); return SKY_ERR_STATE; }
+    int rc;
+    prof_begin(tag, st);
+    if (use_ref) {
+      count_launch(2);
+      rc = launch_gemm2_ref<Epi, BN>(A, epi, w.plain, scratch, M, w.N, w.Kp, st);
+    } else {
+      count_launch();
+      rc = launch_gemm2<Epi, BN, EW>(A, epi, w.img, M, w.N, w.Kp, num_sms, st);
+    }
+    prof_end(tag, st);
+    return rc;
+  }
+  // patch embedding keeps warp producers (im2col + normalisation of the fp32 state)
+  template <int BN, class Prod, class Epi>
+  int gemm_prod(int tag, const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
     int rc;
     prof_begin(tag, st);
     if (use_ref) {
@@ -252,39 +307,39 @@ struct PanguEngine : Engine {
     return rc;
   }
 
-  int run_block(float* x, const Geo& g, const BlockW& b, int roll, int B, const Ws& ws, cudaStream_t st) {
-    const int C = g.C;
-    const long long Mw = (long long)B * g.nWin * WIN_TOK, Mt = (long long)B * g.T;
+  int run_block(float* x, uint8_t* xh, const Geo& g, const BlockW& b, int roll, int B, const Ws& ws, cudaStream_t st) {
+    const int C = g.C, nkb = C / 64;
+    const long long R = (long long)B * g.T;
     int rc;
-    {
-      ProdWindow p{x, g, roll, Mw};
-      EpiStoreF16<false> e{ws.qkv, 3 * C, b.qkv_b, Mw};
-      if ((rc = gemm<192>(KT_QKV, p, e, b.qkv, Mw, ws.scratch, st))) return rc;
+    {  // QKV projection on natural-order tokens
+      AImage A{xh, xh, nkb, 0};
+      Epi2F16<false, false> e{ws.qkv, 3 * C, 0, b.qkv_b};
+      if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
     }
     {
       dim3 grid(g.heads, (unsigned)(B * g.nWin));
       prof_begin(KT_ATTN, st);
-      k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.att, b.bias_tab, g, roll,
+      k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.atth, nkb, b.bias_tab, b.qkv_b, g, roll,
                                                                   rsqrtf(32.f), cfg.mask_value);
       prof_end(KT_ATTN, st);
       count_launch();
       SKY_CUDA_OK(cudaGetLastError());
     }
-    {
-      ProdPlainF16 p{ws.att, C, Mw, C};
-      EpiLnResidual e{x, C, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps, Mw, 1, g, roll};
-      rc = C == 192 ? gemm<192>(KT_PROJ, p, e, b.proj, Mw, ws.scratch, st) : gemm<384>(KT_PROJ, p, e, b.proj, Mw, ws.scratch, st);
+    {  // projection + LayerNorm + residual
+      AImage A{ws.atth, ws.atth, nkb, 0};
+      Epi2F32Img<true, true> e{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
+      rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
+                    : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
       if (rc) return rc;
     }
-    {
-      ProdPlainF32 p{x, C, Mt, C};
-      EpiStoreF16<true> e{ws.hid, 4 * C, b.fc1_b, Mt};
-      if ((rc = gemm<192>(KT_FC1, p, e, b.fc1, Mt, ws.scratch, st))) return rc;
-    }
-    {
-      ProdPlainF16 p{ws.hid, 4 * C, Mt, 4 * C};
-      EpiLnResidual e{x, C, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps, Mt, 0, g, 0};
-      rc = C == 192 ? gemm<192>(KT_FC2, p, e, b.fc2, Mt, ws.scratch, st) : gemm<384>(KT_FC2, p, e, b.fc2, Mt, ws.scratch, st);
+    {  // MLP
+      AImage A{xh, xh, nkb, 0};
+      Epi2F16<true, true> e{reinterpret_cast<__half*>(ws.hidh), 0, 4 * nkb, b.fc1_b};
+      if ((rc = gemm2<192, 8>(KT_FC1, A, e, b.fc1, R, ws.scratch, st))) return rc;
+      AImage A2{ws.hidh, ws.hidh, 4 * nkb, 0};
+      Epi2F32Img<true, true> e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      rc = C == 192 ? gemm2<192, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st)
+                    : gemm2<384, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st);
       if (rc) return rc;
     }
     return 0;
@@ -292,10 +347,10 @@ struct PanguEngine : Engine {
 
   int step(const float* x_in, float* x_out, int B, void* wsp, size_t ws_bytes, cudaStream_t st) override {
     if (!loaded) { set_error("weights not loaded"); return SKY_ERR_STATE; }
-    if (cfg.dim != 192) { set_error("engine kernels are instantiated for dim=192 (got %d)", cfg.dim); return SKY_ERR_ARG; }
     Ws ws = carve(wsp, B);
     if (ws_bytes < ws.total) { set_error("workspace too small: %zu < %zu", ws_bytes, ws.total); return SKY_ERR_ARG; }
     const int C = cfg.dim, HW = g1.H * g1.W, nzt = g1.Z - 1;
+    const long long R1 = (long long)B * g1.T, R2 = (long long)B * g2.T;
     int rc;
     // test tap: SKY_STOP_AFTER=<stage> returns early so debug_copy can read the token buffers
     // (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3)
@@ -305,65 +360,56 @@ struct PanguEngine : Engine {
     {
       long long M = (long long)B * nzt * HW;
       ProdEmbedUpper p{x_in, mean, stdv, cfg.nlat, cfg.nlon, cfg.n_levels, 5, nch, g1.H, g1.W, nzt, M};
-      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW};
-      if ((rc = gemm<192>(KT_EMBED, p, e, embed_u, M, ws.scratch, st))) return rc;
+      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW, ws.x1h, C / 64};
+      if ((rc = gemm_prod<192>(KT_EMBED, p, e, embed_u, M, ws.scratch, st))) return rc;
       long long Ms = (long long)B * HW;
       ProdEmbedSurf ps{x_in, masks, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 4, 3, g1.H, g1.W, Ms};
-      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW};
-      if ((rc = gemm<192>(KT_EMBED, ps, es, embed_s, Ms, ws.scratch, st))) return rc;
+      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW, ws.x1h, C / 64};
+      if ((rc = gemm_prod<192>(KT_EMBED, ps, es, embed_s, Ms, ws.scratch, st))) return rc;
     }
     if (stop == 0) return 0;
-    // ---- layer 0 ----
     for (size_t i = 0; i < blocks[0].size(); ++i)
-      if ((rc = run_block(ws.x1, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
+      if ((rc = run_block(ws.x1, ws.x1h, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
     if (stop == 1) return 0;
     prof_begin(KT_COPY, st);
-    SKY_CUDA_OK(cudaMemcpyAsync(ws.skip, ws.x1, (size_t)B * g1.T * C * 4, cudaMemcpyDeviceToDevice, st));
+    SKY_CUDA_OK(cudaMemcpyAsync(ws.skiph, ws.x1h, ws.x1h_bytes, cudaMemcpyDeviceToDevice, st));
     prof_end(KT_COPY, st);
     // ---- down-sample ----
     {
-      long long rows = (long long)B * g2.T;
       prof_begin(KT_DOWN, st);
-      k_down_merge_ln<24><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ws.x1, ws.hid, down_g, down_b, cfg.ln_eps, g1.Z,
-                                                                   g1.H, g1.W, C, g2.H, g2.W, rows);
+      k_down_merge_ln<24><<<(unsigned)((R2 + 7) / 8), 256, 0, st>>>(ws.x1, ws.hidh, down_g, down_b, cfg.ln_eps, g1.H,
+                                                                 g1.W, C, g2.H, g2.W, R2);
       prof_end(KT_DOWN, st);
       count_launch();
       SKY_CUDA_OK(cudaGetLastError());
-      ProdPlainF16 p{ws.hid, 4 * C, rows, 4 * C};
-      EpiStoreF32 e{ws.x2, 2 * C, nullptr, rows, 0, 0, 0, 0};
-      if ((rc = gemm<192>(KT_DOWN, p, e, down, rows, ws.scratch, st))) return rc;
+      AImage A{ws.hidh, ws.hidh, 4 * C / 64, 0};
+      Epi2F32Img<false, false> e{ws.x2, 2 * C, ws.x2h, 2 * C / 64, nullptr, nullptr, nullptr, 0.f};
+      if ((rc = gemm2<192, 8>(KT_DOWN, A, e, down, R2, ws.scratch, st))) return rc;
     }
     if (stop == 2) return 0;
     for (int li = 1; li <= 2; ++li) {
       for (size_t i = 0; i < blocks[li].size(); ++i)
-        if ((rc = run_block(ws.x2, g2, blocks[li][i], (int)(i & 1), B, ws, st))) return rc;
+        if ((rc = run_block(ws.x2, ws.x2h, g2, blocks[li][i], (int)(i & 1), B, ws, st))) return rc;
       if (stop == 2 + li) return 0;
     }
     // ---- up-sample ----
     {
-      long long rows = (long long)B * g2.T;
-      ProdPlainF32 p{ws.x2, 2 * C, rows, 2 * C};
-      EpiUpShuffleLn e{ws.hid, C, up_g, up_b, cfg.ln_eps, rows, g1.Z, g1.H, g1.W, g2.H, g2.W};
-      if ((rc = gemm<192>(KT_UP, p, e, up1, rows, ws.scratch, st))) return rc;
-      long long M = (long long)B * g1.T;
-      ProdPlainF16 p2{ws.hid, C, M, C};
-      EpiStoreF32 e2{ws.x1, C, nullptr, M, 0, 0, 0, 0};
-      if ((rc = gemm<192>(KT_UP, p2, e2, up2, M, ws.scratch, st))) return rc;
+      AImage A{ws.x2h, ws.x2h, 2 * C / 64, 0};
+      Epi2UpShuffle e{ws.hidh, C / 64, C, up_g, up_b, cfg.ln_eps, nullptr, g1.H, g1.W, g2.H, g2.W};
+      if ((rc = gemm2<192, 8>(KT_UP, A, e, up1, R2, ws.scratch, st))) return rc;
+      AImage A2{ws.hidh, ws.hidh, C / 64, 0};
+      Epi2F32Img<false, false> e2{ws.x1, C, ws.x1h, C / 64, nullptr, nullptr, nullptr, 0.f};
+      if ((rc = gemm2<192, 8>(KT_UP, A2, e2, up2, R1, ws.scratch, st))) return rc;
     }
     if (stop == 5) return 0;
     for (size_t i = 0; i < blocks[3].size(); ++i)
-      if ((rc = run_block(ws.x1, g1, blocks[3][i], (int)(i & 1), B, ws, st))) return rc;
+      if ((rc = run_block(ws.x1, ws.x1h, g1, blocks[3][i], (int)(i & 1), B, ws, st))) return rc;
     if (stop == 6) return 0;
-    // ---- patch recovery ----
+    // ---- patch recovery: concat(skip, x) along K, one GEMM for upper-air + surface ----
     {
-      long long M = (long long)B * nzt * HW;
-      ProdConcat p{ws.skip, ws.x1, C, g1.T, HW, 1, nzt, M};
-      EpiRecover e{x_out, rec_u_b, mean, stdv, cfg.nlat, cfg.nlon, nch, 0, cfg.n_levels, 2, g1.H, g1.W, nzt, 160, M};
-      if ((rc = gemm<160>(KT_RECOVER, p, e, rec_u, M, ws.scratch, st))) return rc;
-      long long Ms = (long long)B * HW;
-      ProdConcat ps{ws.skip, ws.x1, C, g1.T, HW, 0, 1, Ms};
-      EpiRecover es{x_out, rec_s_b, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 1, 1, g1.H, g1.W, 1, 64, Ms};
-      if ((rc = gemm<64>(KT_RECOVER, ps, es, rec_s, Ms, ws.scratch, st))) return rc;
+      AImage A{ws.skiph, ws.x1h, C / 64, C / 64};
+      Epi2Recover e{x_out, rec_b, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, cfg.n_levels, g1.H, g1.W, g1.T};
+      if ((rc = gemm2<224, 8>(KT_RECOVER, A, e, rec, R1, ws.scratch, st))) return rc;
     }
     return 0;
   }
@@ -372,10 +418,20 @@ struct PanguEngine : Engine {
     Ws ws = carve(wsp, B);
     const float* src = nullptr;
     uint64_t n = 0;
-    if (!strcmp(what, "tokens1")) { src = ws.x1; n = (uint64_t)B * g1.T * cfg.dim; }
-    else if (!strcmp(what, "skip")) { src = ws.skip; n = (uint64_t)B * g1.T * cfg.dim; }
-    else if (!strcmp(what, "tokens2")) { src = ws.x2; n = (uint64_t)B * g2.T * 2 * cfg.dim; }
-    else { set_error("unknown debug buffer '%s'", what); return SKY_ERR_ARG; }
+    const long long R1 = (long long)B * g1.T, R2 = (long long)B * g2.T;
+    if (!strcmp(what, "tokens1")) { src = ws.x1; n = (uint64_t)R1 * cfg.dim; }
+    else if (!strcmp(what, "tokens2")) { src = ws.x2; n = (uint64_t)R2 * 2 * cfg.dim; }
+    else if (!strcmp(what, "tokens1_h") || !strcmp(what, "tokens2_h") || !strcmp(what, "skip_h")) {
+      // the fp16 operand image, expanded to fp32 rows
+      const bool two = what[6] == '2';
+      const uint8_t* img = two ? ws.x2h : (!strcmp(what, "skip_h") ? ws.skiph : ws.x1h);
+      const long long rows = two ? R2 : R1;
+      const int cols = two ? 2 * cfg.dim : cfg.dim;
+      if ((uint64_t)rows * cols > max_floats) { set_error("destination too small"); return SKY_ERR_ARG; }
+      k_image_to_rows<<<(unsigned)((rows * cols + 255) / 256), 256, 0, st>>>(img, cols / 64, dst, rows, cols);
+      SKY_CUDA_OK(cudaGetLastError());
+      return 0;
+    } else { set_error("unknown debug buffer '%s'", what); return SKY_ERR_ARG; }
     if (n > max_floats) n = max_floats;
     SKY_CUDA_OK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));
     return 0;

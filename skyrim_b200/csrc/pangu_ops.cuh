@@ -189,12 +189,13 @@ struct ProdEmbedSurf {
 // n0 = first column of this tile in the full N, BN = tile width.
 // ======================================================================================
 
-// out_f32[dstrow, n0+col] = acc + bias      (patch embedding, up-sample linear2, down-sample)
+// out_f32[dstrow, n0+col] = acc + bias  (+ the fp16 tile image of the same rows)   (patch embedding)
 struct EpiStoreF32 {
   float* out; int ldo; const float* bias;  // bias may be null
   long long M;
   // dst row = member*T + zoff*HW + (row % rows_per_member); identity when rows_per_member==0
   int T; int HW; int zoff; long long rows_per_member;
+  uint8_t* img; int nkb;  // optional fp16 image (SWIZZLE_128B tiles of 128 rows x 64 cols)
   template <class Acc>
   __device__ void run(Acc& acc, long long row, int n0, int BN) const {
     long long dst = row;
@@ -212,6 +213,19 @@ struct EpiStoreF32 {
             t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
           }
           o[j] = t;
+          v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+        if (img) {
+          const int col = n0 + c;
+          uint8_t* base = img + ((size_t)(dst >> 7) * nkb + (col >> 6)) * 16384;
+          const uint32_t r = (uint32_t)(dst & 127);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_half2(v[8 * j], v[8 * j + 1]); pk.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+            pk.z = pack_half2(v[8 * j + 4], v[8 * j + 5]); pk.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(base + sw128_offset(r, ((col & 63) >> 3) + j)) = pk;
+          }
         }
       }
     }

@@ -1,0 +1,37 @@
+"""Algorithmic work of one 6-h step, per kernel family (the figures bench.py's ``roofline``
+object and DESIGN.md use; derivation in SURVEY.md §8(d)).  FLOPs are 2*MAC of the dense
+contractions; bytes are the mandatory HBM traffic of the family's fused kernel."""
+from __future__ import annotations
+
+from .config import PanguConfig
+
+WIN_TOK = 144
+
+
+def pangu_flops(cfg: PanguConfig) -> dict:
+    C = cfg.dim
+    HW = cfg.H * cfg.W
+    T1, T2 = cfg.Z * HW, cfg.Z * cfg.H2 * cfg.W2
+    nwin1 = (cfg.Z // 2) * (cfg.padded_h(cfg.H) // 6) * (cfg.W // 12)
+    nwin2 = (cfg.Z // 2) * (cfg.padded_h(cfg.H2) // 6) * (cfg.W2 // 12)
+    f = dict(qkv=0.0, attn=0.0, proj=0.0, fc1=0.0, fc2=0.0)
+    for li, depth in enumerate(cfg.depths):
+        c, T, rows = (C, T1, nwin1 * WIN_TOK) if li in (0, 3) else (2 * C, T2, nwin2 * WIN_TOK)
+        f["qkv"] += depth * 2.0 * rows * c * 3 * c
+        f["attn"] += depth * 2.0 * 2.0 * rows * WIN_TOK * c
+        f["proj"] += depth * 2.0 * rows * c * c
+        f["fc1"] += depth * 2.0 * T * c * 4 * c
+        f["fc2"] += depth * 2.0 * T * 4 * c * c
+    f["mlp"] = f["fc1"] + f["fc2"]
+    nzt = cfg.Z - 1
+    f["embed"] = 2.0 * nzt * HW * 160 * C + 2.0 * HW * 112 * C
+    f["recover"] = 2.0 * nzt * HW * 2 * C * 160 + 2.0 * HW * 2 * C * 64
+    f["down"] = 2.0 * T2 * 4 * C * 2 * C
+    f["up"] = 2.0 * T2 * 2 * C * 4 * C + 2.0 * T1 * C * C
+    f["total"] = (f["qkv"] + f["attn"] + f["proj"] + f["fc1"] + f["fc2"] + f["embed"] + f["recover"]
+                  + f["down"] + f["up"])
+    return f
+
+
+def pangu_state_bytes(cfg: PanguConfig) -> int:
+    return cfg.n_channels * cfg.nlat * cfg.nlon * 4
