@@ -18,6 +18,7 @@
 #include "gemm2_ref.cuh"
 #include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
+#include "mlp_fused.cuh"
 
 namespace sky {
 
@@ -115,6 +116,7 @@ struct GemmW {
 };
 struct BlockW {
   GemmW qkv, proj, fc1, fc2;
+  GemmW fc1f;  // fc1 packed in hidden-chunk tiles for the fused MLP kernel
   const float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   float* bias_tab;  // (n_type, heads, 3312)
 };
@@ -219,6 +221,7 @@ struct PanguEngine : Engine {
         if ((rc = pack(b.proj, N("proj.w"), c, c, c, false, st))) return rc;
         if ((rc = pack(b.fc1, N("fc1.w"), 4 * c, c, 192, false, st))) return rc;
         if ((rc = pack(b.fc2, N("fc2.w"), c, 4 * c, c, false, st))) return rc;
+        if ((rc = pack(b.fc1f, N("fc1.w"), 4 * c, c, c == 192 ? MlpCfg<192>::HC : MlpCfg<384>::HC, false, st))) return rc;
         P(b.qkv_b, N("qkv.b"), 3 * c); P(b.proj_b, N("proj.b"), c);
         P(b.fc1_b, N("fc1.b"), 4 * c); P(b.fc2_b, N("fc2.b"), c);
         P(b.ln1_g, N("ln1.g"), c); P(b.ln1_b, N("ln1.b"), c);
@@ -328,11 +331,27 @@ struct PanguEngine : Engine {
     {  // projection + LayerNorm + residual
       AImage A{ws.atth, ws.atth, nkb, 0};
       Epi2F32Img<true, true> e{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
+      static const char* exp_env = getenv("SKY_EXP");  // timing experiments only (results invalid)
+      const int ex = exp_env ? atoi(exp_env) : 0;
+      if (ex == 1) e.img = nullptr;
+      if (ex == 2) {
+        Epi2F32Img<true, false> e3{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
+        rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e3, b.proj, R, ws.scratch, st)
+                      : gemm2<384, 8>(KT_PROJ, A, e3, b.proj, R, ws.scratch, st);
+      } else
       rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
                     : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
       if (rc) return rc;
     }
-    {  // MLP
+    if (!use_ref) {  // fused MLP: fc1 + GELU + fc2 + LayerNorm + residual, hidden stays on the SM
+      Epi2F32Img<true, true> e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      prof_begin(KT_MLP, st);
+      count_launch();
+      rc = C == 192 ? launch_mlp_fused<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
+                    : launch_mlp_fused<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
+      prof_end(KT_MLP, st);
+      if (rc) return rc;
+    } else {  // two plain GEMMs through an HBM-resident hidden image (reference path only)
       AImage A{xh, xh, nkb, 0};
       Epi2F16<true, true> e{reinterpret_cast<__half*>(ws.hidh), 0, 4 * nkb, b.fc1_b};
       if ((rc = gemm2<192, 8>(KT_FC1, A, e, b.fc1, R, ws.scratch, st))) return rc;

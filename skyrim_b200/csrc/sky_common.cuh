@@ -56,12 +56,58 @@ __device__ __forceinline__ float mufu_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+//   gelu(x) = relu(x) - |x| * h(|x|),   h(a) = 0.5 erfc(a / sqrt 2) ~= t (a1 + t (a2 + t a3)) exp(-a^2/2) / 2,
+//   t = 1 / (1 + p a / sqrt 2)
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = mufu_rcp(fmaf(0.47047f, z, 1.0f));
-  const float poly = t * fmaf(t, fmaf(t, 0.7478556f, -0.0958798f), 0.3480242f);
-  const float h = 0.5f * poly * mufu_ex2(-1.4426950408889634f * z * z);  // 0.5 * erfc(z)
-  return x * (x >= 0.f ? 1.0f - h : h);
+  const float nax = -fabsf(x);
+  const float t = mufu_rcp(fmaf(nax, -0.47047f * 0.70710678118654752440f, 1.0f));
+  const float e = mufu_ex2(x * x * (-0.5f * 1.4426950408889634f));
+  const float q = t * fmaf(t, fmaf(t, 0.5f * 0.7478556f, 0.5f * -0.0958798f), 0.5f * 0.3480242f);
+  return fmaf(nax, q * e, fmaxf(x, 0.f));
+}
+// two lanes of the same formula on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100): the
+// epilogue of the fused MLP is issue bound on this function
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t d, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// (x0, x1) <- gelu(x0 + b0), gelu(x1 + b1)
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1, float b0, float b1) {
+  const uint64_t x = add_f32x2(pack_f32x2(x0, x1), pack_f32x2(b0, b1));
+  float y0, y1;
+  unpack_f32x2(x, y0, y1);
+  const float n0 = -fabsf(y0), n1 = -fabsf(y1);
+  const uint64_t nax = pack_f32x2(n0, n1);
+  constexpr float P = -0.47047f * 0.70710678118654752440f, EC = -0.5f * 1.4426950408889634f;
+  float u0, u1, a0, a1;
+  unpack_f32x2(fma_f32x2(nax, pack_f32x2(P, P), pack_f32x2(1.f, 1.f)), u0, u1);
+  unpack_f32x2(mul_f32x2(mul_f32x2(x, x), pack_f32x2(EC, EC)), a0, a1);
+  const uint64_t t = pack_f32x2(mufu_rcp(u0), mufu_rcp(u1));
+  const uint64_t e = pack_f32x2(mufu_ex2(a0), mufu_ex2(a1));
+  uint64_t q = fma_f32x2(t, pack_f32x2(0.5f * 0.7478556f, 0.5f * 0.7478556f), pack_f32x2(0.5f * -0.0958798f, 0.5f * -0.0958798f));
+  q = fma_f32x2(t, q, pack_f32x2(0.5f * 0.3480242f, 0.5f * 0.3480242f));
+  q = mul_f32x2(mul_f32x2(q, t), e);
+  const uint64_t r = fma_f32x2(nax, q, pack_f32x2(fmaxf(y0, 0.f), fmaxf(y1, 0.f)));
+  unpack_f32x2(r, x0, x1);
 }
 
 // Byte offset of element (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile whose rows
@@ -98,9 +144,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait.  try_wait suspends the warp in hardware up to the time hint, so a waiting
+// role warp does not burn issue slots of the epilogue warps that share its scheduler
+// (the v1 C-level spin loop cost ~30% of all executed instructions: profiles/r1_mlp_v1.md).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SKY_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra SKY_DONE_%=;\n\t"
+      "bra SKY_WAIT_%=;\n\t"
+      "SKY_DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680)
+      : "memory");
 }
 // generic-proxy smem writes -> visible to the async proxy (UMMA / bulk copy)
 __device__ __forceinline__ void fence_proxy_async_smem() {
