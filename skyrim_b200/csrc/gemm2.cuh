@@ -47,7 +47,7 @@ struct G2Cfg {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = G2_A_BYTES + B_BYTES;
   static constexpr int PATCH_BYTES = EPI_WARPS * G2_PATCH_FLOATS * 4;
-  static constexpr int VEC_BYTES = 512 * 4;  // smem copy of the bias (LN epilogues), <= 512 floats
+  static constexpr int VEC_BYTES = 3 * 512 * 4;  // smem copies of bias | gamma | beta (LN epilogues), <= 512 floats each
   static constexpr int FIXED = 1024 /*align*/ + 256 /*barriers*/ + PATCH_BYTES + VEC_BYTES;
   static constexpr int MAXS = (232448 - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = MAXS > 6 ? 6 : MAXS;
@@ -69,7 +69,8 @@ struct EpiCtx {
   int n0;           // first column of the tile in the full N
   int part, nparts; // column-chunk partition among the warps sharing a lane quarter
   float* patch;     // [32][33] floats, private to the warp
-  const float* sbias;  // smem copy of bias[0..BLOCK_N) (valid when the epilogue asked for it)
+  uint32_t patch_s;    // the same patch as a shared-space address
+  uint32_t svec_s;     // shared-space address of bias[512] | gamma[512] | beta[512] (LN epilogues)
 };
 
 struct AccTmem2 {
@@ -86,7 +87,7 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* patches = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   float* sbias = patches + EPI_WARPS * G2_PATCH_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 512);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 3 * 512);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -103,8 +104,10 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
     mbar_fence_init();
   }
   if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
-  if (Epi::kNeedsBias && threadIdx.x < EPI_WARPS * 32)
-    for (int i = threadIdx.x; i < BLOCK_N; i += EPI_WARPS * 32) sbias[i] = epi.bias[i];
+  if constexpr (Epi::kNeedsBias) if (threadIdx.x < EPI_WARPS * 32)
+    for (int i = threadIdx.x; i < BLOCK_N; i += EPI_WARPS * 32) {
+      sbias[i] = epi.bias[i]; sbias[512 + i] = epi.gamma[i]; sbias[1024 + i] = epi.beta[i];
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,7 +167,8 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
     EpiCtx ctx;
     ctx.M = M; ctx.lane = lane; ctx.part = part; ctx.nparts = EPI_WARPS / 4;
     ctx.patch = patches + warp * G2_PATCH_FLOATS;
-    ctx.sbias = sbias;
+    ctx.patch_s = smem_u32(ctx.patch);
+    ctx.svec_s = smem_u32(sbias);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it % Cfg::NBUF;
@@ -216,21 +220,38 @@ __device__ __forceinline__ void patch_put(float* patch, int lane, const float (&
 #pragma unroll
   for (int j = 0; j < 32; ++j) patch[lane * G2_PATCH_LD + j] = v[j];
 }
+__device__ __forceinline__ void patch_put_s(uint32_t patch_s, int lane, const float (&v)[32]) {
+  const uint32_t a = patch_s + lane * (G2_PATCH_LD * 4);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) sts_f32(a + 4 * j, v[j]);
+}
+// 8 consecutive floats of patch row rr starting at column c8 -> 8 halves
+__device__ __forceinline__ uint4 patch_get_h8(uint32_t patch_s, int rr, int c8) {
+  const uint32_t a = patch_s + (rr * G2_PATCH_LD + c8) * 4;
+  uint4 pk;
+  pk.x = pack_half2(lds_f32(a), lds_f32(a + 4));
+  pk.y = pack_half2(lds_f32(a + 8), lds_f32(a + 12));
+  pk.z = pack_half2(lds_f32(a + 16), lds_f32(a + 20));
+  pk.w = pack_half2(lds_f32(a + 24), lds_f32(a + 28));
+  return pk;
+}
 
 // fp16 output, optional GELU: row-major [M, ldo] (kImage = false) or tile image with nkb
-// k-blocks per row tile (kImage = true).
+// k-blocks per row tile (kImage = true).  16-byte stores: lane -> (row = it*8 + lane/4,
+// 8-column chunk = lane%4), so four lanes cover 64 contiguous bytes of one row.
 template <bool kGelu, bool kImage>
 struct Epi2F16 {
   static constexpr bool kNeedsBias = false;
   __half* out; int ldo; int nkb; const float* bias;
+  const float* gamma = nullptr; const float* beta = nullptr;  // unused (uniform epilogue interface)
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& x) const {
-    const int cp = 2 * (x.lane & 15), hr = x.lane >> 4;
+    const int rsub = x.lane >> 2, ch = x.lane & 3;
+    const uint32_t r0 = (uint32_t)(x.row0 & 127);
     for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
       float v[32];
       acc.load32(c, v);
       // bias + activation in the row domain: 32 independent dependency chains per thread
-      // (doing it after the re-tiling left 2 chains per thread and was latency bound)
       const float4* bp = reinterpret_cast<const float4*>(bias + x.n0 + c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -239,20 +260,23 @@ struct Epi2F16 {
       }
       if (kGelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1], 0.f, 0.f);
       }
-      patch_put(x.patch, x.lane, v);
+      patch_put_s(x.patch_s, x.lane, v);
       __syncwarp();
-      const int col = x.n0 + c + cp;
-#pragma unroll 8
-      for (int it = 0; it < 16; ++it) {
-        const int rr = 2 * it + hr;
-        const float y0 = x.patch[rr * G2_PATCH_LD + cp], y1 = x.patch[rr * G2_PATCH_LD + cp + 1];
-        const long long row = x.row0 + rr;
-        if (row < x.M) {
-          uint32_t pk = pack_half2(y0, y1);
-          if (kImage) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(out) + img_offset(row, col, nkb)) = pk;
-          else *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pk;
+      const int col = x.n0 + c;  // first column of the chunk
+      uint8_t* ibase = nullptr;
+      if (kImage)
+        ibase = reinterpret_cast<uint8_t*>(out) + ((size_t)(x.row0 >> 7) * nkb + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + rsub;
+        const uint4 pk = patch_get_h8(x.patch_s, rr, ch * 8);
+        if (x.row0 + rr < x.M) {
+          if (kImage)
+            *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
+          else
+            *reinterpret_cast<uint4*>(out + (x.row0 + rr) * ldo + col + ch * 8) = pk;
         }
       }
       __syncwarp();
@@ -263,6 +287,8 @@ struct Epi2F16 {
 // xf32[row, n0+col] (=|+=) f(acc)  and the fp16 tile image of the new rows.
 //   kLn:       y = LayerNorm(acc + bias) * gamma + beta  (tile spans the feature width: n0 == 0)
 //   kResidual: x += y, else x = y  (bias, if any, is applied when !kLn as well)
+// Global traffic is 128-bit: lane -> (row = it*4 + lane/8, float4 column group = lane%8), i.e.
+// eight lanes cover one 128-byte row segment.  bias / gamma / beta come from shared memory.
 template <bool kLn, bool kResidual>
 struct Epi2F32Img {
   static constexpr bool kNeedsBias = kLn;
@@ -271,15 +297,20 @@ struct Epi2F32Img {
   const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& e) const {
+    const int rsub4 = e.lane >> 3, c4 = e.lane & 7;   // fp32 phase
+    const int rsub8 = e.lane >> 2, ch = e.lane & 3;   // fp16 image phase
+    const int step = 32 * e.nparts;
+    const long long rows_left = e.M - e.row0;          // >= 32 for every tile but the last
+    float* xp = x + e.row0 * ldx + e.n0 + c4 * 4;
     // the residual rows are prefetched one column chunk ahead (the first chunk before the
-    // statistics pass): the epilogue is bound by the latency of these loads, not by bandwidth
-    float xin[32];
+    // statistics pass): the epilogue is bound by the latency of these loads
+    float4 xin[8];
     if (kResidual) {
-      const int col0 = e.n0 + e.part * 32 + e.lane;
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const long long row = e.row0 + rr;
-        xin[rr] = (row < e.M && e.part * 32 < BN) ? x[row * ldx + col0] : 0.f;
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        xin[it] = (rr < rows_left && e.part * 32 < BN) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     float mean = 0.f, rstd = 1.f;
@@ -290,7 +321,7 @@ struct Epi2F32Img {
         acc.load32(c, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float4 b = *reinterpret_cast<const float4*>(e.sbias + c + j);
+          const float4 b = lds_f32x4(e.svec_s + (c + j) * 4);
           float y0 = v[j] + b.x, y1 = v[j + 1] + b.y, y2 = v[j + 2] + b.z, y3 = v[j + 3] + b.w;
           s += (y0 + y1) + (y2 + y3);
           ss += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
@@ -299,54 +330,64 @@ struct Epi2F32Img {
       mean = s / BN;
       rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
     }
-    const int cp = 2 * (e.lane & 15), hr = e.lane >> 4;
-    const int step = 32 * e.nparts;
+    const uint32_t r0 = (uint32_t)(e.row0 & 127);
     for (int c = e.part * 32; c < BN; c += step) {
       float v[32];
       acc.load32(c, v);
       if (kLn) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (v[j] + e.sbias[c + j] - mean) * rstd;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = lds_f32x4(e.svec_s + (c + j) * 4);
+          v[j] = (v[j] + b.x - mean) * rstd; v[j + 1] = (v[j + 1] + b.y - mean) * rstd;
+          v[j + 2] = (v[j + 2] + b.z - mean) * rstd; v[j + 3] = (v[j + 3] + b.w - mean) * rstd;
+        }
       }
-      patch_put(e.patch, e.lane, v);
+      patch_put_s(e.patch_s, e.lane, v);
       __syncwarp();
-      const int col = e.n0 + c + e.lane;
-      float g = 1.f, b = 0.f;
-      if (kLn) { g = __ldg(gamma + col); b = __ldg(beta + col); }
-      else if (bias) b = __ldg(bias + col);
-      float xnext[32];
+      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kLn) {
+        g = lds_f32x4(e.svec_s + (512 + c + c4 * 4) * 4);
+        b = lds_f32x4(e.svec_s + (1024 + c + c4 * 4) * 4);
+      } else if (bias) {
+        b = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
+      }
+      float4 xnext[8];
       if (kResidual) {
         const bool more = c + step < BN;
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          const long long row = e.row0 + rr;
-          xnext[rr] = (more && row < e.M) ? x[row * ldx + col + step] : 0.f;
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub4;
+          xnext[it] = (more && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c + step)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const long long row = e.row0 + rr;
-        float y = e.patch[rr * G2_PATCH_LD + e.lane] * g + b;
-        if (kResidual) y += xin[rr];
-        if (row < e.M) x[row * ldx + col] = y;
-        e.patch[rr * G2_PATCH_LD + e.lane] = y;
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        const uint32_t pa = e.patch_s + (rr * G2_PATCH_LD + c4 * 4) * 4;
+        float4 y;
+        y.x = lds_f32(pa) * g.x + b.x; y.y = lds_f32(pa + 4) * g.y + b.y;
+        y.z = lds_f32(pa + 8) * g.z + b.z; y.w = lds_f32(pa + 12) * g.w + b.w;
+        if (kResidual) { y.x += xin[it].x; y.y += xin[it].y; y.z += xin[it].z; y.w += xin[it].w; }
+        if (rr < rows_left) *reinterpret_cast<float4*>(xp + (size_t)rr * ldx + c) = y;
+        sts_f32(pa, y.x); sts_f32(pa + 4, y.y); sts_f32(pa + 8, y.z); sts_f32(pa + 12, y.w);
       }
       __syncwarp();
       if (img) {
-        const int colp = e.n0 + c + cp;
-#pragma unroll 8
-        for (int it = 0; it < 16; ++it) {
-          const int rr = 2 * it + hr;
-          const long long row = e.row0 + rr;
-          if (row < e.M)
-            *reinterpret_cast<uint32_t*>(img + img_offset(row, colp, nkb)) =
-                pack_half2(e.patch[rr * G2_PATCH_LD + cp], e.patch[rr * G2_PATCH_LD + cp + 1]);
+        const int col = e.n0 + c;
+        uint8_t* ibase = img + ((size_t)(e.row0 >> 7) * nkb + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rsub8;
+          const uint4 pk = patch_get_h8(e.patch_s, rr, ch * 8);
+          if (rr < rows_left)
+            *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
         }
       }
       __syncwarp();
       if (kResidual) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) xin[rr] = xnext[rr];
+        for (int it = 0; it < 8; ++it) xin[it] = xnext[it];
       }
     }
   }

@@ -70,17 +70,18 @@ struct AccScratch2 {
 template <class Epi, int BLOCK_N>
 __global__ void __launch_bounds__(128) k_epi2_ref(Epi epi, const float* __restrict__ scratch, long long M, int N) {
   __shared__ float patches[4 * G2_PATCH_FLOATS];
-  __shared__ float sbias[512];
+  __shared__ float sbias[3 * 512];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n0 = blockIdx.y * BLOCK_N;
-  if (Epi::kNeedsBias)
-    for (int i = threadIdx.x; i < BLOCK_N; i += 128) sbias[i] = epi.bias[i];
+  if constexpr (Epi::kNeedsBias)
+    for (int i = threadIdx.x; i < BLOCK_N; i += 128) { sbias[i] = epi.bias[i]; sbias[512 + i] = epi.gamma[i]; sbias[1024 + i] = epi.beta[i]; }
   __syncthreads();
   EpiCtx ctx;
   ctx.row0 = ((long long)blockIdx.x * 4 + warp) * 32;
   ctx.M = M; ctx.lane = lane; ctx.n0 = n0; ctx.part = 0; ctx.nparts = 1;
   ctx.patch = patches + warp * G2_PATCH_FLOATS;
-  ctx.sbias = sbias;
+  ctx.patch_s = smem_u32(ctx.patch);
+  ctx.svec_s = smem_u32(sbias);
   const long long row = ctx.row0 + lane;
   AccScratch2 acc{row < M ? scratch + row * N + n0 : nullptr};
   epi.template run<BLOCK_N>(acc, ctx);

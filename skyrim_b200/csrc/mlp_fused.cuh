@@ -30,7 +30,7 @@ struct MlpCfg {
   static constexpr int NH = C / 192;
   static constexpr int W1_ITEM = HC * 128;
   static constexpr int W2_ITEM = 192 * 128;
-  static constexpr int S1 = C == 192 ? 8 : 5;  // ring depth is what hides the ~2 us L2 latency of a weight item
+  static constexpr int S1 = C == 192 ? 7 : 4;  // ring depth is what hides the ~2 us L2 latency of a weight item
   static constexpr int S2 = C == 192 ? 3 : 2;
   static constexpr int A_BYTES = NKB * G2_A_BYTES;
   static constexpr int HID_BYTES = HKB * G2_A_BYTES;
@@ -40,7 +40,8 @@ struct MlpCfg {
   static constexpr int PATCH_BYTES = 8 * G2_PATCH_FLOATS * 4;   // LN patches alias the hidden buffers
   static constexpr int HID_REGION = ((2 * HID_BYTES > PATCH_BYTES ? 2 * HID_BYTES : PATCH_BYTES) + 1023) / 1024 * 1024;
   static constexpr int OFF_VEC = OFF_HID + HID_REGION;          // b1[4C] b2[C] floats
-  static constexpr int OFF_BAR = OFF_VEC + 5 * C * 4;
+  static constexpr int OFF_LNV = OFF_VEC + 4 * C * 4;           // bias2 | gamma | beta, 512 floats apart
+  static constexpr int OFF_BAR = OFF_LNV + 3 * 512 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int ACC2_COL = 2 * HC;
   static constexpr int THREADS = 352;
@@ -65,7 +66,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   uint8_t* w2_s = smem + Cfg::OFF_W2;
   uint8_t* hid_s = smem + Cfg::OFF_HID;
   float* b1s = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
-  float* b2s = b1s + 4 * C;
+  float* lnv = reinterpret_cast<float*>(smem + Cfg::OFF_LNV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
@@ -96,7 +97,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   }
   if (warp == 9) tmem_alloc<512>(tmem_ptr);
   for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) b1s[i] = b1[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = epi.bias[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { lnv[i] = epi.bias[i]; lnv[512 + i] = epi.gamma[i]; lnv[1024 + i] = epi.beta[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -220,7 +221,8 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
     EpiCtx ctx;
     ctx.M = M; ctx.lane = lane; ctx.part = part; ctx.nparts = 2; ctx.n0 = 0;
     ctx.patch = reinterpret_cast<float*>(hid_s) + warp * G2_PATCH_FLOATS;
-    ctx.sbias = b2s;
+    ctx.patch_s = smem_u32(ctx.patch);
+    ctx.svec_s = smem_u32(lnv);
     uint32_t cnt = 0, tph = 0;
     constexpr int COLS_PER_WARP = Cfg::HC / 2;
     for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x, tph ^= 1) {

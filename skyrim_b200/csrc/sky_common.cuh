@@ -110,6 +110,22 @@ __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1, float b0, floa
   unpack_f32x2(r, x0, x1);
 }
 
+// explicit shared-space accessors (a generic LD/ST through a pointer kept in a struct costs a
+// long-scoreboard round trip; these compile to LDS/STS)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
 // Byte offset of element (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile whose rows
 // are 128 bytes (64 halves): Swizzle<3,4,3> — chunk index XOR (row mod 8).
 __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {

@@ -191,3 +191,83 @@ def synthetic_state(names, nlat: int, nlon: int, seed: int = 0) -> np.ndarray:
 
 def n_params(weights) -> int:
     return int(sum(int(np.prod(v.shape)) for v in weights.values()))
+
+
+# ----------------------------------------------------------------------------------------
+# SFNO (FourCastNet-v2-small)
+# ----------------------------------------------------------------------------------------
+def sfno_param_shapes(cfg: SFNOConfig) -> "OrderedDict[str, tuple]":
+    E, Cin = cfg.embed, cfg.n_channels
+    s = OrderedDict()
+    s["norm.mean"] = (Cin,)
+    s["norm.std"] = (Cin,)
+    s["enc.fc1.w"] = (E, Cin)
+    s["enc.fc1.b"] = (E,)
+    s["enc.fc2.w"] = (E, E)
+    s["enc.fc2.b"] = (E,)
+    s["pos_embed"] = (E, cfg.nlat, cfg.nlon)
+    for i in range(cfg.layers):
+        p = f"blk{i}."
+        s[p + "norm0.g"] = (E,)
+        s[p + "norm0.b"] = (E,)
+        s[p + "spec.w"] = (cfg.lmax, E, E, 2)        # [l, out, in, (re, im)]
+        s[p + "inner.w"] = (E, E)
+        s[p + "inner.b"] = (E,)
+        s[p + "norm1.g"] = (E,)
+        s[p + "norm1.b"] = (E,)
+        s[p + "fc1.w"] = (cfg.mlp_ratio * E, E)
+        s[p + "fc1.b"] = (cfg.mlp_ratio * E,)
+        s[p + "fc2.w"] = (E, cfg.mlp_ratio * E)
+        s[p + "fc2.b"] = (E,)
+    s["dec.fc1.w"] = (E, E + Cin)
+    s["dec.fc1.b"] = (E,)
+    s["dec.fc2.w"] = (Cin, E)
+    s["dec.fc2.b"] = (Cin,)
+    return s
+
+
+def make_sfno_weights(cfg: SFNOConfig, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Synthetic SFNO parameters.  Linear layers are variance preserving (std 1/sqrt(fan_in))
+    so that 40 autoregressive steps neither explode nor collapse; the spectral (dhconv)
+    weights are complex normal with std 1/sqrt(2 E) per component."""
+    from .config import FCNV2_CHANNELS
+    out = OrderedDict()
+    mu, sd = channel_stats(FCNV2_CHANNELS)
+    for name, shape in sfno_param_shapes(cfg).items():
+        if name == "norm.mean":
+            a = mu
+        elif name == "norm.std":
+            a = sd
+        elif name.endswith((".g",)):
+            g, b = _ln(seed, name[:-2], shape[0])
+            out[name], out[name[:-1] + "b"] = g, b
+            continue
+        elif name.endswith(("norm0.b", "norm1.b")):
+            continue
+        elif name == "pos_embed":
+            a = _tn(seed, name, shape, std=0.1)
+        elif name.endswith("spec.w"):
+            a = _rng(seed, name).standard_normal(shape, dtype=np.float32) * np.float32(1.0 / np.sqrt(2.0 * cfg.embed))
+        elif name.endswith(".b"):
+            a = _tn(seed, name, shape, std=0.02)
+        else:
+            a = _tn(seed, name, shape, std=0.9 / np.sqrt(shape[-1]))
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return OrderedDict((k, out[k]) for k in sfno_param_shapes(cfg))
+
+
+def sfno_tables(cfg: SFNOConfig) -> "OrderedDict[str, np.ndarray]":
+    """SHT / DFT tables the engine consumes as extra arena entries (fp32)."""
+    from .sht import dft_matrices, sht_tables
+    t = OrderedDict()
+    fwd_big, inv_big = sht_tables(cfg.nlat, cfg.lmax, cfg.mmax, "equiangular")
+    fwd_int, inv_int = sht_tables(cfg.h, cfg.lmax, cfg.mmax, "legendre-gauss")
+    t["sht.fwd_big"] = fwd_big.astype(np.float32)     # [m, l, k]
+    t["sht.inv_big"] = inv_big.astype(np.float32)     # [m, k, l]
+    t["sht.fwd_int"] = fwd_int.astype(np.float32)
+    t["sht.inv_int"] = inv_int.astype(np.float32)
+    for tag, n in (("big", cfg.nlon), ("int", cfg.w)):
+        f, i = dft_matrices(n, cfg.mmax)
+        t[f"dft.fwd_{tag}"] = f.astype(np.float32)    # [(m, re/im), j]
+        t[f"dft.inv_{tag}"] = i.astype(np.float32)    # [j, (m, re/im)]
+    return t
