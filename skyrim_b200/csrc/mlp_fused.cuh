@@ -55,7 +55,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
             const Epi2F32Img<true, true> epi,   // x (fp32), xh out image, b2, gamma, beta
             const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
             const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
-            const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg) {
+            const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg, int expflags) {
   using Cfg = MlpCfg<C>;
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define SKY_T(i, stmt) do { long long _t0 = dbg ? clock64() : 0; stmt; if (dbg) tacc[i] += clock64() - _t0; } while (0)
@@ -223,6 +223,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
     ctx.patch = reinterpret_cast<float*>(hid_s) + warp * G2_PATCH_FLOATS;
     ctx.patch_s = smem_u32(ctx.patch);
     ctx.svec_s = smem_u32(lnv);
+    const uint32_t b1s_s = smem_u32(b1s);
     uint32_t cnt = 0, tph = 0;
     constexpr int COLS_PER_WARP = Cfg::HC / 2;
     for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x, tph ^= 1) {
@@ -240,9 +241,16 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
           float v[32];
           tmem_ld32(taddr + g * 32, v);
           const int hc = part * COLS_PER_WARP + g * 32;          // column inside the chunk
-          const float* bb = b1s + j * Cfg::HC + hc;
+          const uint32_t bb = b1s_s + (j * Cfg::HC + hc) * 4;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) gelu_erf_x2(v[i], v[i + 1], bb[i], bb[i + 1]);
+          if (!(expflags & 1)) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = lds_f32x4(bb + i * 4);
+            gelu_erf_x2(v[i], v[i + 1], b4.x, b4.y);
+            gelu_erf_x2(v[i + 2], v[i + 3], b4.z, b4.w);
+          }
+          }
           uint8_t* kbase = hbuf + (hc >> 6) * G2_A_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -266,7 +274,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
       long long _tl = dbg ? clock64() : 0;
       ctx.row0 = (long long)mt * 128 + q * 32;
       AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::ACC2_COL};
-      epi.template run<C>(acc, ctx);
+      if (!(expflags & 2)) epi.template run<C>(acc, ctx);
       tc_fence_before();
       // the LN patches alias the hidden buffers: no epilogue warp may start the next tile's
       // GELU stores before every warp has left its patch
@@ -302,7 +310,8 @@ int launch_mlp_fused(const uint8_t* xh_in, const Epi2F32Img<true, true>& epi, co
   }
   const int tiles = (int)((M + 127) / 128);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(xh_in, epi, W1img, W2img, b1, M, tiles, dbg);
+  static const int expflags = getenv("SKY_MLP_EXP") ? atoi(getenv("SKY_MLP_EXP")) : 0;  // timing experiments only
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(xh_in, epi, W1img, W2img, b1, M, tiles, dbg, expflags);
   if (dbg && dbg_runs < 2) {
     ++dbg_runs;
     cudaDeviceSynchronize();

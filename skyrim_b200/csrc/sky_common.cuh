@@ -43,9 +43,12 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// erf-GELU (PyTorch default): x * Phi(x) with erfc from Abramowitz-Stegun 7.1.25
-// (|abs err| <= 2.5e-5 on erfc, i.e. <= 1.3e-5 relative on the result — 20x below the fp16
-// rounding the value receives next).  ~12 instructions, two of them MUFU (rcp, ex2).
+// erf-GELU (PyTorch default), division free:
+//     gelu(x) = relu(x) - |x| h(|x|),   h(a) = Phi(-a) = 0.5 erfcx(a/sqrt 2) exp(-a^2/2)
+// with 0.5 erfcx(a/sqrt 2) replaced by a degree-7 polynomial fitted on [0, 6] under the weight
+// exp(-a^2/2) (tools/fit_gelu.py): max abs error 1.2e-5, 20x below the fp16 rounding the value
+// receives next.  One MUFU (ex2) per element — the earlier rcp+ex2 form made the fused-MLP
+// epilogue MUFU bound (16 lanes/clk/SM on sm_100).
 __device__ __forceinline__ float mufu_rcp(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -56,17 +59,25 @@ __device__ __forceinline__ float mufu_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-//   gelu(x) = relu(x) - |x| * h(|x|),   h(a) = 0.5 erfc(a / sqrt 2) ~= t (a1 + t (a2 + t a3)) exp(-a^2/2) / 2,
-//   t = 1 / (1 + p a / sqrt 2)
+#define SKY_GELU_C0 4.999848197e-01f
+#define SKY_GELU_C1 -3.985058804e-01f
+#define SKY_GELU_C2 2.469212325e-01f
+#define SKY_GELU_C3 -1.237550324e-01f
+#define SKY_GELU_C4 4.792390463e-02f
+#define SKY_GELU_C5 -1.291761998e-02f
+#define SKY_GELU_C6 2.073202457e-03f
+#define SKY_GELU_C7 -1.453669241e-04f
+#define SKY_GELU_EC (-0.5f * 1.4426950408889634f)
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float nax = -fabsf(x);
-  const float t = mufu_rcp(fmaf(nax, -0.47047f * 0.70710678118654752440f, 1.0f));
-  const float e = mufu_ex2(x * x * (-0.5f * 1.4426950408889634f));
-  const float q = t * fmaf(t, fmaf(t, 0.5f * 0.7478556f, 0.5f * -0.0958798f), 0.5f * 0.3480242f);
-  return fmaf(nax, q * e, fmaxf(x, 0.f));
+  const float a = fabsf(x);
+  const float e = mufu_ex2(x * x * SKY_GELU_EC);
+  float p = SKY_GELU_C7;
+  p = fmaf(p, a, SKY_GELU_C6); p = fmaf(p, a, SKY_GELU_C5); p = fmaf(p, a, SKY_GELU_C4);
+  p = fmaf(p, a, SKY_GELU_C3); p = fmaf(p, a, SKY_GELU_C2); p = fmaf(p, a, SKY_GELU_C1);
+  p = fmaf(p, a, SKY_GELU_C0);
+  return fmaf(-a, p * e, fmaxf(x, 0.f));
 }
-// two lanes of the same formula on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100): the
-// epilogue of the fused MLP is issue bound on this function
+// two lanes of the same formula on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100)
 __device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
@@ -93,20 +104,19 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
 // (x0, x1) <- gelu(x0 + b0), gelu(x1 + b1)
 __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1, float b0, float b1) {
   const uint64_t x = add_f32x2(pack_f32x2(x0, x1), pack_f32x2(b0, b1));
-  float y0, y1;
+  float y0, y1, a0, a1;
   unpack_f32x2(x, y0, y1);
-  const float n0 = -fabsf(y0), n1 = -fabsf(y1);
-  const uint64_t nax = pack_f32x2(n0, n1);
-  constexpr float P = -0.47047f * 0.70710678118654752440f, EC = -0.5f * 1.4426950408889634f;
-  float u0, u1, a0, a1;
-  unpack_f32x2(fma_f32x2(nax, pack_f32x2(P, P), pack_f32x2(1.f, 1.f)), u0, u1);
-  unpack_f32x2(mul_f32x2(mul_f32x2(x, x), pack_f32x2(EC, EC)), a0, a1);
-  const uint64_t t = pack_f32x2(mufu_rcp(u0), mufu_rcp(u1));
+  unpack_f32x2(mul_f32x2(mul_f32x2(x, x), pack_f32x2(SKY_GELU_EC, SKY_GELU_EC)), a0, a1);
   const uint64_t e = pack_f32x2(mufu_ex2(a0), mufu_ex2(a1));
-  uint64_t q = fma_f32x2(t, pack_f32x2(0.5f * 0.7478556f, 0.5f * 0.7478556f), pack_f32x2(0.5f * -0.0958798f, 0.5f * -0.0958798f));
-  q = fma_f32x2(t, q, pack_f32x2(0.5f * 0.3480242f, 0.5f * 0.3480242f));
-  q = mul_f32x2(mul_f32x2(q, t), e);
-  const uint64_t r = fma_f32x2(nax, q, pack_f32x2(fmaxf(y0, 0.f), fmaxf(y1, 0.f)));
+  const uint64_t ax = pack_f32x2(fabsf(y0), fabsf(y1));
+#define SKY_P2(c) pack_f32x2(c, c)
+  uint64_t p = fma_f32x2(SKY_P2(SKY_GELU_C7), ax, SKY_P2(SKY_GELU_C6));
+  p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C5)); p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C4));
+  p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C3)); p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C2));
+  p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C1)); p = fma_f32x2(p, ax, SKY_P2(SKY_GELU_C0));
+#undef SKY_P2
+  const uint64_t q = mul_f32x2(p, e);
+  const uint64_t r = fma_f32x2(pack_f32x2(-fabsf(y0), -fabsf(y1)), q, pack_f32x2(fmaxf(y0, 0.f), fmaxf(y1, 0.f)));
   unpack_f32x2(r, x0, x1);
 }
 

@@ -1,0 +1,36 @@
+"""Skyrim(name).predict(...) end to end on the GPU engine (small grid)."""
+import datetime
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_pangu_predict_api(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle.pangu_ref import PanguRef, rel_err_per_channel
+    from skyrim_b200 import Skyrim
+    from skyrim_b200.config import PANGU_CHANNELS, pangu_small
+    from skyrim_b200.weights import make_pangu_weights
+    cfg = pangu_small(41, 96)
+    w = make_pangu_weights(cfg, 0)
+    sk = Skyrim("pangu", ic_source="synthetic", cfg=cfg, weights=w)
+    pred, paths = sk.predict(date="20240507", time="0000", lead_time=13, save=True,
+                             save_config=dict(output_dir=str(tmp_path), file_type="netcdf"))
+    # reference semantics: lead time floored to 12 h -> 2 steps, one file per step, dims time/channel/lat/lon
+    assert len(paths) == 2 and set(pred.prediction.dims) == {"time", "channel", "lat", "lon"}
+    assert list(pred.channels.values) == PANGU_CHANNELS
+    assert pred.prediction.shape == (2, 69, 41, 96)
+    ref = PanguRef(cfg, w)
+    x0 = sk.model.data_source[datetime.datetime(2024, 5, 7)].values
+    y2 = ref.step(ref.step(x0)).numpy()
+    e = rel_err_per_channel(pred.prediction.values[1], y2)
+    assert e.max() < 2e-3, e.max()
+    assert np.isfinite(pred.wind_speed(lat=10.0, lon=20.0, pressure_level=850))
+    # forecast(): all steps in one device-resident generator, first slice is the IC
+    da = sk.forecast(datetime.datetime(2024, 5, 7), n_steps=2, channels=["t2m", "u10m"])
+    assert da.shape == (3, 2, 41, 96)
+    np.testing.assert_allclose(da.values[0, 0], x0[PANGU_CHANNELS.index("t2m")])
