@@ -92,7 +92,9 @@ def cpu_reference(steps: int, warmup: int, band_nlat: int):
     from skyrim_b200.config import PANGU_CHANNELS, pangu_full, pangu_small
     from skyrim_b200.roofline import pangu_flops
     from skyrim_b200.weights import make_pangu_weights, synthetic_state
-    cores = os.cpu_count() or 1
+    # torch's CPU kernels stop scaling (and oversubscribe) beyond a few dozen threads on the
+    # big bench hosts; `cores` reports the threads actually used
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     full, band = pangu_full(), pangu_small(band_nlat, 1440)
     frac = pangu_flops(band)["total"] / pangu_flops(full)["total"]

@@ -1,0 +1,90 @@
+"""CPU tests of the SFNO restatement: SHT tables, truncated-DFT matrices, oracle precision."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.pangu_ref import rel_err_per_channel
+from oracle.sfno_ref import SFNORef
+from skyrim_b200.config import FCNV2_CHANNELS, sfno_full, sfno_small
+from skyrim_b200.sht import RealSHT, clenshaw_curtis, dft_matrices, legendre_gauss, legpoly
+from skyrim_b200.weights import make_sfno_weights, sfno_param_shapes, sfno_tables, synthetic_state
+
+
+def test_quadrature_rules():
+    for n in (13, 32):
+        x, w = clenshaw_curtis(n)
+        assert abs(w.sum() - 2.0) < 1e-13 and abs((w * x ** 2).sum() - 2.0 / 3.0) < 1e-12
+        x, w = legendre_gauss(n)
+        assert abs(w.sum() - 2.0) < 1e-13 and abs((w * x ** 4).sum() - 2.0 / 5.0) < 1e-12
+
+
+def test_legendre_orthonormality():
+    x, w = legendre_gauss(40)
+    p = legpoly(17, 16, x)
+    for m in (0, 3, 9):
+        g = 2 * np.pi * np.einsum("lk,jk,k->lj", p[m], p[m], w)
+        ll = np.arange(16)
+        mask = (ll[:, None] >= m) & (ll[None, :] >= m)
+        assert np.abs(g - np.eye(16))[mask].max() < 1e-12
+
+
+@pytest.mark.parametrize("nlat,nlon,grid", [(49, 96, "equiangular"), (16, 32, "legendre-gauss")])
+def test_sht_roundtrip_and_dft_matrices(nlat, nlon, grid):
+    lmax, mmax = 16, 17
+    s = RealSHT(nlat, nlon, lmax, mmax, grid)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((lmax, mmax)) + 1j * rng.standard_normal((lmax, mmax))
+    X[:, 0] = X[:, 0].real
+    for m in range(mmax):
+        X[:m, m] = 0
+    if mmax - 1 == nlon // 2:
+        X[:, -1] = 0
+    x = s.inverse(X)
+    assert np.abs(s.forward(x) - X).max() < 1e-12
+    f, i = dft_matrices(nlon, mmax)
+    F = x @ f.T
+    ref = 2 * np.pi * np.fft.rfft(x, axis=-1, norm="forward")[:, :mmax]
+    assert np.abs((F[:, 0::2] + 1j * F[:, 1::2]) - ref).max() < 1e-12
+    assert np.abs(F @ i.T - np.fft.irfft(ref, n=nlon, axis=-1, norm="forward")).max() < 1e-11
+
+
+def test_full_config_shapes():
+    c = sfno_full()
+    assert (c.h, c.w, c.lmax, c.mmax) == (240, 480, 240, 241)
+    sh = sfno_param_shapes(c)
+    assert sh["blk0.spec.w"] == (240, 384, 384, 2) and sh["dec.fc1.w"] == (384, 457)
+    assert len(FCNV2_CHANNELS) == 73
+
+
+def test_oracle_precision_and_stability():
+    cfg = sfno_small(49, 96, embed=64, layers=3)
+    w = make_sfno_weights(cfg, 0)
+    x0 = synthetic_state(FCNV2_CHANNELS, cfg.nlat, cfg.nlon, 0)
+    y64 = SFNORef(cfg, w, torch.float64).step(x0).numpy()
+    y32 = SFNORef(cfg, w, torch.float32).step(x0).numpy()
+    assert rel_err_per_channel(y32, y64).max() < 1e-5
+    t = sfno_tables(cfg)
+    assert t["sht.fwd_big"].shape == (cfg.mmax, cfg.lmax, cfg.nlat) and t["dft.inv_int"].shape == (cfg.w, 2 * cfg.mmax)
+    # autoregressive use neither explodes nor collapses
+    r = SFNORef(cfg, w)
+    x = torch.from_numpy(x0)
+    mu, sd = r.w["norm.mean"][:, None, None], r.w["norm.std"][:, None, None]
+    for _ in range(4):
+        x = r.step(x)
+    s = float(((x - mu) / sd).std())
+    assert 0.1 < s < 3.0, s
+
+
+def test_three_term_fp16_split_is_fp32_grade():
+    """hi + lo fp16 split used for the SFNO GEMM operands: a*b ~= ah*bh + al*bh + ah*bl."""
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((64, 256)).astype(np.float32)
+    b = (rng.standard_normal((256, 48)) * 0.05).astype(np.float32)
+    ah, bh = a.astype(np.float16), b.astype(np.float16)
+    al = (a - ah.astype(np.float32)).astype(np.float16)
+    bl = (b - bh.astype(np.float32)).astype(np.float16)
+    f = lambda u, v: u.astype(np.float32) @ v.astype(np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    one = np.abs(f(ah, bh) - exact).max() / np.abs(exact).max()
+    three = np.abs(f(ah, bh) + f(al, bh) + f(ah, bl) - exact).max() / np.abs(exact).max()
+    assert one > 1e-4 and three < 3e-6, (one, three)
