@@ -1,0 +1,212 @@
+// Batched, K-segmented variant of the TMA-fed tcgen05 GEMM (gemm2.cuh), used by the SFNO path:
+//
+//   for b in batches:  D_b[M, N] = A_b[M, Ktot] * W_b[N, Ktot]^T      -> fused epilogue
+//
+// The A operand is a concatenation along K of up to 6 image segments, which is how the
+// 3-term fp16 split (a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo) and the decoder's
+// concat(x, input) are expressed without touching the kernel: A = [hi | lo | hi] (the same
+// image twice), W = one image packed as [hi | hi | lo].  Every batch has its own A and W
+// images at fixed byte strides (Legendre transforms: one per zonal wavenumber m; the spectral
+// channel mixing: one per degree l).
+#pragma once
+#include "gemm2.cuh"
+
+namespace sky {
+
+struct AOperand {
+  const uint8_t* seg[6];
+  int nkb[6];                 // k-blocks of each segment
+  long long batch_stride[6];  // bytes between batches of each segment
+  int nseg;
+  int m_tiles_per_batch;      // row tiles of one batch inside a segment image
+  __device__ const uint8_t* kblock(int batch, int mt, int kb) const {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      if (s < nseg) {
+        if (kb < nkb[s]) return seg[s] + (size_t)batch * batch_stride[s] + ((size_t)mt * nkb[s] + kb) * G2_A_BYTES;
+        kb -= nkb[s];
+      }
+    }
+    return seg[0];
+  }
+};
+
+struct EpiCtxB : EpiCtx {
+  int batch;
+};
+
+template <class Epi, int BLOCK_N, int EPI_WARPS>
+__global__ void __launch_bounds__((EPI_WARPS + 2) * 32, 1)
+k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg, long long w_batch_stride,
+               long long M, int num_kb, int num_m_tiles, int num_n_tiles, int batches) {
+  using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* patches = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  float* sbias = patches + EPI_WARPS * G2_PATCH_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 3 * 512);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int tiles_per_batch = num_m_tiles * num_n_tiles;
+  const long long num_tiles = (long long)tiles_per_batch * batches;
+  constexpr int LOADER = EPI_WARPS, MMAW = EPI_WARPS + 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == LOADER) {
+    int s = 0; uint32_t ph = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
+      const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+      const uint8_t* wsrc = Wimg + (size_t)b * w_batch_stride + (size_t)nt * num_kb * Cfg::B_BYTES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (lane == 0) {
+          uint8_t* dst = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          bulk_g2s(dst, A.kblock(b, mt, kb), G2_A_BYTES, &full[s]);
+          bulk_g2s(dst + G2_A_BYTES, wsrc + (size_t)kb * Cfg::B_BYTES, Cfg::B_BYTES, &full[s]);
+        }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == MMAW) {
+    constexpr uint32_t idesc = make_idesc_f16(G2_BLOCK_M, Cfg::N_INST);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % Cfg::NBUF;
+      const uint32_t use = (uint32_t)(it / Cfg::NBUF);
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc_sw128(a_addr + k * 32);
+#pragma unroll
+            for (int ni = 0; ni < Cfg::N_SPLIT; ++ni) {
+              const uint64_t db = make_desc_sw128(b_addr + ni * Cfg::N_INST * 128 + k * 32);
+              tc_mma_f16(d_tmem + ni * Cfg::N_INST, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[s]);
+          if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3, part = warp >> 2;
+    EpiCtxB ctx;
+    ctx.M = M; ctx.lane = lane; ctx.part = part; ctx.nparts = EPI_WARPS / 4;
+    ctx.patch = patches + warp * G2_PATCH_FLOATS;
+    ctx.patch_s = smem_u32(ctx.patch);
+    ctx.svec_s = smem_u32(sbias);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % Cfg::NBUF;
+      const uint32_t use = (uint32_t)(it / Cfg::NBUF);
+      const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
+      ctx.batch = b;
+      ctx.row0 = (long long)(t / num_n_tiles) * G2_BLOCK_M + q * 32;
+      ctx.n0 = (t % num_n_tiles) * BLOCK_N;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N)};
+      epi.template run<BLOCK_N>(acc, ctx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == MMAW) {
+    __syncwarp();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <class Epi, int BLOCK_N, int EPI_WARPS>
+int launch_gemm_batched(const AOperand& A, const Epi& epi, const uint8_t* Wimg, long long w_batch_stride, long long M,
+                        int N, int Ktot, int batches, int num_sms, cudaStream_t st) {
+  using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
+  auto kern = k_gemm_batched<Epi, BLOCK_N, EPI_WARPS>;
+  static bool configured = false;
+  if (!configured) {
+    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_m_tiles = (int)((M + G2_BLOCK_M - 1) / G2_BLOCK_M);
+  const int num_n_tiles = N / BLOCK_N;
+  const long long tiles = (long long)num_m_tiles * num_n_tiles * batches;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(A, epi, Wimg, w_batch_stride, M, Ktot / 64, num_m_tiles, num_n_tiles,
+                                                   batches);
+  SKY_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// out[batch][row, n0+col] (=|+=) acc (+ bias[col]) — fp32 row-major, 128-bit accesses on full
+// row segments (same re-tiling as Epi2F32Img).  kAccumulate adds to what the buffer holds
+// (pre-filled by the caller with a residual / positional / spectral term).
+template <bool kAccumulate>
+struct EpiF32Batched {
+  static constexpr bool kNeedsBias = false;
+  float* out; int ldo; long long batch_stride /*floats*/; const float* bias /*may be null*/;
+  int n_valid;  // columns >= n_valid are padding and are not stored
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtxB& e) const {
+    const int rsub4 = e.lane >> 3, c4 = e.lane & 7;
+    const int step = 32 * e.nparts;
+    const long long rows_left = e.M - e.row0;
+    float* xp = out + (size_t)e.batch * batch_stride + e.row0 * ldo + e.n0 + c4 * 4;
+    for (int c = e.part * 32; c < BN; c += step) {
+      float v[32];
+      acc.load32(c, v);
+      patch_put_s(e.patch_s, e.lane, v);
+      __syncwarp();
+      const int col = e.n0 + c + c4 * 4;
+      if (col < n_valid) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub4;
+          if (rr < rows_left) {
+            const uint32_t pa = e.patch_s + (rr * G2_PATCH_LD + c4 * 4) * 4;
+            float4 y = make_float4(lds_f32(pa) + b.x, lds_f32(pa + 4) + b.y, lds_f32(pa + 8) + b.z, lds_f32(pa + 12) + b.w);
+            float4* dst = reinterpret_cast<float4*>(xp + (size_t)rr * ldo + c);
+            if (kAccumulate) { const float4 o = *dst; y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w; }
+            *dst = y;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
+}  // namespace sky
