@@ -24,14 +24,14 @@ namespace sky {
 template <int C>
 struct MlpCfg {
   static constexpr int NKB = C / 64;
-  static constexpr int HC = 64;
+  static constexpr int HC = C == 192 ? 128 : 64;  // N of GEMM1: an SS-mode MMA re-reads its 4 KB A slice per K=16 step, so small N is smem-bandwidth bound
   static constexpr int NCH = 4 * C / HC;
   static constexpr int HKB = HC / 64;
   static constexpr int NH = C / 192;
   static constexpr int W1_ITEM = HC * 128;
   static constexpr int W2_ITEM = 192 * 128;
-  static constexpr int S1 = C == 192 ? 7 : 4;  // ring depth is what hides the ~2 us L2 latency of a weight item
-  static constexpr int S2 = C == 192 ? 3 : 2;
+  static constexpr int S1 = C == 192 ? 3 : 4;  // ring depth is what hides the ~2 us L2 latency of a weight item
+  static constexpr int S2 = 2;
   static constexpr int A_BYTES = NKB * G2_A_BYTES;
   static constexpr int HID_BYTES = HKB * G2_A_BYTES;
   static constexpr int OFF_W1 = A_BYTES;
