@@ -150,13 +150,31 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = pangu_full()
+    sfno = args.model == "sfno"
+    if sfno:
+        from skyrim_b200.config import FCNV2_CHANNELS as CHANNELS, sfno_full
+        from skyrim_b200.roofline import sfno_flops
+        from skyrim_b200.timeloop import SFNOTimeLoop as Loop
+        from skyrim_b200.weights import make_sfno_weights, sfno_param_shapes, sfno_tables
+        cfg = sfno_full()
+    else:
+        CHANNELS, Loop = PANGU_CHANNELS, PanguTimeLoop
+        cfg = pangu_full()
     M = args.members_per_gpu
     # ---- weights: built on rank 0, ONE NCCL broadcast of the fp32 arena, repacked on each device ----
-    w = make_pangu_weights(cfg, 0) if rank == 0 else None
+    if sfno:
+        w = None
+        if rank == 0:
+            w = make_sfno_weights(cfg, 0); w.update(sfno_tables(cfg))
+    else:
+        w = make_pangu_weights(cfg, 0) if rank == 0 else None
     if world > 1:
         from skyrim_b200.weights import pangu_param_shapes
-        shapes = pangu_param_shapes(cfg)
+        if sfno:
+            shapes = dict(sfno_param_shapes(cfg))
+            shapes.update({k: v.shape for k, v in sfno_tables(cfg).items()})
+        else:
+            shapes = pangu_param_shapes(cfg)
         if rank == 0:
             arena_h, manifest = pack_arena(w)
             arena = torch.from_numpy(arena_h).to(dev)
@@ -170,12 +188,13 @@ def run_ours(args):
     else:
         eng = StepEngine(cfg, local)
         eng.load_weights(w)
-    loop = PanguTimeLoop(eng)
+    loop = Loop(eng)
+    del w
 
     # ---- synthetic initial conditions: base state + per-member Philox perturbation (K11) ----
-    base = torch.from_numpy(synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0))
+    base = torch.from_numpy(synthetic_state(CHANNELS, cfg.nlat, cfg.nlon, 0))
     x = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
-    sigma = torch.from_numpy(channel_stats(PANGU_CHANNELS)[1]).to(dev)
+    sigma = torch.from_numpy(channel_stats(CHANNELS)[1]).to(dev)
     perturb_ic(x, sigma, 0.05, seed=0, member0=rank * M)
     y = torch.empty_like(x)
 
@@ -230,29 +249,32 @@ def run_ours(args):
     value = world * M * 1000.0 / ms_step
 
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not sfno:
         cb = cpu_reference(1, 0, 91)
 
     if rank == 0:
         peaks = _peaks()
-        fl = pangu_flops(cfg)
+        fl = sfno_flops(cfg) if sfno else pangu_flops(cfg)
         fam_flops = M * fl.get(dominant, 0.0)
         n_l = dom[1] / args.steps
         avg_ms = dom[0] / max(dom[1], 1)
         achieved = fam_flops / max(n_l, 1) / (avg_ms * 1e-3) / 1e12 if fam_flops else None
-        sbytes = pangu_state_bytes(cfg) * M
+        sbytes = cfg.n_channels * cfg.nlat * cfg.nlon * 4 * M
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, LN, softmax",
+            "vs_baseline": None, "dtype": ("f16 hi+lo split operands (3-term) / f32 accumulate (tcgen05 kind::f16), f32 state" if sfno else
+                      "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, LN, softmax"),
             "data": "synthetic",
-            "config": {"workload": "Pangu 7-day rollout (chained 6-h steps), synthetic (69,721,1440) IC, state "
-                                   "resident in HBM", "members_per_gpu": M, "members_total": world * M,
-                       "l2": "inputs larger than L2 (287 MB state + >2 GB activations streamed per step)",
-                       "weights": "synthetic seed 0 (64 M parameters)", "finite": finite},
+            "config": {"workload": ("FourCastNet-v2 SFNO rollout (chained 6-h steps), 73-channel synthetic (73,721,1440) IC, "
+                                    "state resident in HBM" if sfno else
+                                    "Pangu 7-day rollout (chained 6-h steps), synthetic (69,721,1440) IC, state "
+                                    "resident in HBM"), "members_per_gpu": M, "members_total": world * M,
+                       "l2": "inputs larger than L2 (state 0.3 GB + >2 GB activations streamed per step)",
+                       "weights": "synthetic seed 0", "finite": finite},
             "e2e": {"value": world * M * 1000.0 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes,
-                    "path": "PanguTimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host"},
+                    "path": "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dominant, "achieved": achieved,
@@ -272,10 +294,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=28)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members-per-gpu", type=int, default=1)
+    ap.add_argument("--model", default="pangu", choices=["pangu", "sfno"],
+                    help="pangu (default, the headline workload) or sfno (FourCastNet-v2 73-channel rollout)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -13,7 +13,7 @@ namespace sky {
 constexpr int ATT_THREADS = 96;
 constexpr int ATT_LDS = 40;  // halves per smem row (32 + 8 pad): conflict-free ldmatrix
 constexpr int ATT_TABLE = (2 * WW - 1) * WH * WH * WZ * WZ;  // 3312
-constexpr int ATT_SMEM_BYTES = 3 * WIN_TOK * ATT_LDS * 2 + ATT_TABLE * 4 + 2 * WIN_TOK * 4 + WIN_TOK * 8;
+constexpr int ATT_SMEM_BYTES = 3 * WIN_TOK * ATT_LDS * 2 + ATT_TABLE * 2 + 2 * WIN_TOK * 4 + WIN_TOK * 8;  // 43.5 KB: 5 CTAs per SM
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
@@ -39,13 +39,13 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // (tokens, C) (A operand of the projection GEMM), again in natural order.
 __global__ void __launch_bounds__(ATT_THREADS)
 k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img, int att_nkb,
-                   const float* __restrict__ bias_tab, const float* __restrict__ qkv_bias, Geo g, int roll,
+                   const __half* __restrict__ bias_tab, const float* __restrict__ qkv_bias, Geo g, int roll,
                    float scale, float mask_value) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* Qs = reinterpret_cast<__half*>(att_smem);
   __half* Ks = Qs + WIN_TOK * ATT_LDS;
   __half* Vs = Ks + WIN_TOK * ATT_LDS;
-  float* Bs = reinterpret_cast<float*>(Vs + WIN_TOK * ATT_LDS);
+  __half* Bs = Vs + WIN_TOK * ATT_LDS;  // fp16 table slice (values ~0.03: rounding 1.5e-5 abs)
   int* colpart = reinterpret_cast<int*>(Bs + ATT_TABLE);  // per key token: column part of the table index (+64)
   int* colflag = colpart + WIN_TOK;                       // per key token: seam side flags (z: 1, lat: 2)
   long long* tok = reinterpret_cast<long long*>(colflag + WIN_TOK);
@@ -65,8 +65,8 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
     colpart[j] = part + 64;  // +64 keeps it non-negative (the row part carries -64)
     colflag[j] = (zj >= WZ - SZ ? 1 : 0) | (hj >= WH - SH ? 2 : 0);
   }
-  const float* bsrc = bias_tab + ((long long)type * g.heads + head) * ATT_TABLE;
-  for (int i = tid; i < ATT_TABLE / 4; i += ATT_THREADS) cp_async16(Bs + 4 * i, bsrc + 4 * i);
+  const __half* bsrc = bias_tab + ((long long)type * g.heads + head) * ATT_TABLE;
+  for (int i = tid; i < ATT_TABLE / 8; i += ATT_THREADS) cp_async16(Bs + 8 * i, bsrc + 8 * i);
   __syncthreads();
   // ---- stage Q, K, V (64 B per token each) ----
   for (int i = tid; i < WIN_TOK * 12; i += ATT_THREADS) {
@@ -121,15 +121,17 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
       rowpart[1] = zi * ((2 * WW - 1) * WH * WH) + hi * (2 * WW - 1) + wi + (WW - 1) - 64;
       rflag[1] = (zi >= WZ - SZ ? 1 : 0) | (hi >= WH - SH ? 2 : 0);
     }
-    const float* B0 = Bs + rowpart[0];
-    const float* B1 = Bs + rowpart[1];
+    const __half* B0 = Bs + rowpart[0];
+    const __half* B1 = Bs + rowpart[1];
     float mx0 = -INFINITY, mx1 = -INFINITY;
     if (fmask == 0) {
+      // packed fp32x2 (FFMA2): the kernel is issue bound on this loop and the exp loop below
+      const uint64_t sl22 = pack_f32x2(sl2, sl2);
 #pragma unroll
       for (int nt = 0; nt < 18; ++nt) {
         const int2 cp2 = *reinterpret_cast<const int2*>(colpart + nt * 8 + 2 * (lane & 3));
-        s[nt][0] = fmaf(s[nt][0], sl2, B0[cp2.x]); s[nt][1] = fmaf(s[nt][1], sl2, B0[cp2.y]);
-        s[nt][2] = fmaf(s[nt][2], sl2, B1[cp2.x]); s[nt][3] = fmaf(s[nt][3], sl2, B1[cp2.y]);
+        unpack_f32x2(fma_f32x2(pack_f32x2(s[nt][0], s[nt][1]), sl22, pack_f32x2(__half2float(B0[cp2.x]), __half2float(B0[cp2.y]))), s[nt][0], s[nt][1]);
+        unpack_f32x2(fma_f32x2(pack_f32x2(s[nt][2], s[nt][3]), sl22, pack_f32x2(__half2float(B1[cp2.x]), __half2float(B1[cp2.y]))), s[nt][2], s[nt][3]);
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -139,10 +141,10 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
         const int j = nt * 8 + 2 * (lane & 3);
         const int2 cp2 = *reinterpret_cast<const int2*>(colpart + j);
         const int f0 = colflag[j], f1 = colflag[j + 1];
-        s[nt][0] = fmaf(s[nt][0], sl2, B0[cp2.x]) + (((rflag[0] ^ f0) & fmask) ? mask_l2 : 0.f);
-        s[nt][1] = fmaf(s[nt][1], sl2, B0[cp2.y]) + (((rflag[0] ^ f1) & fmask) ? mask_l2 : 0.f);
-        s[nt][2] = fmaf(s[nt][2], sl2, B1[cp2.x]) + (((rflag[1] ^ f0) & fmask) ? mask_l2 : 0.f);
-        s[nt][3] = fmaf(s[nt][3], sl2, B1[cp2.y]) + (((rflag[1] ^ f1) & fmask) ? mask_l2 : 0.f);
+        s[nt][0] = fmaf(s[nt][0], sl2, __half2float(B0[cp2.x])) + (((rflag[0] ^ f0) & fmask) ? mask_l2 : 0.f);
+        s[nt][1] = fmaf(s[nt][1], sl2, __half2float(B0[cp2.y])) + (((rflag[0] ^ f1) & fmask) ? mask_l2 : 0.f);
+        s[nt][2] = fmaf(s[nt][2], sl2, __half2float(B1[cp2.x])) + (((rflag[1] ^ f0) & fmask) ? mask_l2 : 0.f);
+        s[nt][3] = fmaf(s[nt][3], sl2, __half2float(B1[cp2.y])) + (((rflag[1] ^ f1) & fmask) ? mask_l2 : 0.f);
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -151,13 +153,23 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
+    float sum0, sum1;
+    {
+      const uint64_t nm0 = pack_f32x2(-mx0, -mx0), nm1 = pack_f32x2(-mx1, -mx1);
+      uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-      s[nt][0] = mufu_ex2(s[nt][0] - mx0); s[nt][1] = mufu_ex2(s[nt][1] - mx0);
-      s[nt][2] = mufu_ex2(s[nt][2] - mx1); s[nt][3] = mufu_ex2(s[nt][3] - mx1);
-      sum0 += s[nt][0] + s[nt][1];
-      sum1 += s[nt][2] + s[nt][3];
+      for (int nt = 0; nt < 18; ++nt) {
+        float d0, d1, d2, d3;
+        unpack_f32x2(add_f32x2(pack_f32x2(s[nt][0], s[nt][1]), nm0), d0, d1);
+        unpack_f32x2(add_f32x2(pack_f32x2(s[nt][2], s[nt][3]), nm1), d2, d3);
+        s[nt][0] = mufu_ex2(d0); s[nt][1] = mufu_ex2(d1);
+        s[nt][2] = mufu_ex2(d2); s[nt][3] = mufu_ex2(d3);
+        acc0 = add_f32x2(acc0, pack_f32x2(s[nt][0], s[nt][1]));
+        acc1 = add_f32x2(acc1, pack_f32x2(s[nt][2], s[nt][3]));
+      }
+      float a, b;
+      unpack_f32x2(acc0, a, b); sum0 = a + b;
+      unpack_f32x2(acc1, a, b); sum1 = a + b;
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);

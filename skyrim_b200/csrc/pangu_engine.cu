@@ -52,14 +52,14 @@ __global__ void k_pack_weight(const float* __restrict__ W, int Nsrc, int K, int 
 
 // earth-specific bias (3312, n_type, heads) -> (n_type, heads, 3312), pre-scaled by log2(e)
 // (the attention kernel computes its softmax with exp2)
-__global__ void k_pack_bias_table(const float* __restrict__ src, float* __restrict__ dst, int L, int n_type,
+__global__ void k_pack_bias_table(const float* __restrict__ src, __half* __restrict__ dst, int L, int n_type,
                                   int heads) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (long long)L * n_type * heads;
   if (idx >= tot) return;
   int l = (int)(idx % L);
   long long th = idx / L;  // type*heads + head
-  dst[idx] = src[(long long)l * n_type * heads + th] * 1.4426950408889634f;
+  dst[idx] = __float2half_rn(src[(long long)l * n_type * heads + th] * 1.4426950408889634f);
 }
 
 // DownSample front end: 2x2 (lat, lon) merge + zero pad + LayerNorm(4C) -> fp16 tile image.
@@ -118,7 +118,7 @@ struct BlockW {
   GemmW qkv, proj, fc1, fc2;
   GemmW fc1f;  // fc1 packed in hidden-chunk tiles for the fused MLP kernel
   const float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  float* bias_tab;  // (n_type, heads, 3312)
+  __half* bias_tab;  // (n_type, heads, 3312), fp16, pre-scaled by log2 e
 };
 
 struct PanguEngine : Engine {
@@ -229,7 +229,7 @@ struct PanguEngine : Engine {
         const float* bt;
         long long tot = (long long)ATT_TABLE * n_type * heads;
         P(bt, N("bias_table"), tot);
-        b.bias_tab = dalloc<float>((size_t)tot);
+        b.bias_tab = dalloc<__half>((size_t)tot);
         if (!b.bias_tab) return SKY_ERR_NOMEM;
         k_pack_bias_table<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(bt, b.bias_tab, ATT_TABLE, n_type, heads);
         count_launch();

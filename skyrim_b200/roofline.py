@@ -3,7 +3,7 @@ object and DESIGN.md use; derivation in SURVEY.md §8(d)).  FLOPs are 2*MAC of t
 contractions; bytes are the mandatory HBM traffic of the family's fused kernel."""
 from __future__ import annotations
 
-from .config import PanguConfig
+from .config import PanguConfig, SFNOConfig
 
 WIN_TOK = 144
 
@@ -35,3 +35,25 @@ def pangu_flops(cfg: PanguConfig) -> dict:
 
 def pangu_state_bytes(cfg: PanguConfig) -> int:
     return cfg.n_channels * cfg.nlat * cfg.nlon * 4
+
+
+def sfno_flops(cfg: SFNOConfig) -> dict:
+    """SURVEY.md §8(d) formulae (Legendre contractions, per-l channel mixing, pixel MLPs); the
+    longitude DFT is counted as an FFT (negligible) although the engine runs it as a GEMM, and
+    the 3-term fp16 split triples the executed tensor work without changing these figures."""
+    E, Cin, L = cfg.embed, cfg.n_channels, cfg.layers
+    P1, P2 = cfg.nlat * cfg.nlon, cfg.h * cfg.w
+    lm = cfg.lmax * cfg.mmax
+    f = {}
+    f["sfno_enc"] = 2.0 * P1 * (Cin * E + E * E)
+    f["sfno_dec"] = 2.0 * P1 * ((E + Cin) * E + E * Cin)
+    leg_big, leg_int = 4.0 * cfg.nlat * lm * E, 4.0 * cfg.h * lm * E
+    f["sfno_sht"] = leg_big + (L - 1) * leg_int
+    # inverse transforms: mixed spectrum of every block + the resampled residual of the two grid-changing blocks
+    f["sfno_isht"] = (L - 1) * leg_int + leg_big + leg_int + leg_big
+    f["sfno_spec"] = L * 8.0 * lm * E * E
+    mlp_int = 2.0 * P2 * (E * E + 2 * cfg.mlp_ratio * E * E)
+    mlp_big = 2.0 * P1 * (E * E + 2 * cfg.mlp_ratio * E * E)
+    f["sfno_mlp"] = (L - 1) * mlp_int + mlp_big
+    f["total"] = sum(f.values())
+    return f
