@@ -175,6 +175,7 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
       const uint32_t use = (uint32_t)(it / Cfg::NBUF);
       ctx.row0 = (long long)(tile / num_n_tiles) * G2_BLOCK_M + q * 32;
       ctx.n0 = (tile % num_n_tiles) * BLOCK_N;
+      if constexpr (Epi::kNeedsBias) epi.template prefetch<BLOCK_N>(ctx);  // LN + residual epilogues
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N)};
@@ -295,6 +296,18 @@ struct Epi2F32Img {
   float* x; int ldx;            // fp32 row-major
   uint8_t* img; int nkb;        // fp16 image of the same rows (may be null)
   const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
+  // Pull this warp's residual rows into L2 ahead of time.  A register-destination prefetch does
+  // not work here: tcgen05.wait::ld also waits for the thread's outstanding global loads, so
+  // every TMEM read in run() would expose the full HBM latency (profiles/r1_mlp.md).
+  template <int BN>
+  __device__ void prefetch(const EpiCtx& e) const {
+    if (!kResidual) return;
+    const long long row = e.row0 + e.lane;
+    if (row >= e.M) return;
+    const char* p = reinterpret_cast<const char*>(x + row * ldx + e.n0);
+#pragma unroll
+    for (int i = e.part; i < BN * 4 / 128; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+  }
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& e) const {
     const int rsub4 = e.lane >> 3, c4 = e.lane & 7;   // fp32 phase
@@ -321,7 +334,7 @@ struct Epi2F32Img {
         acc.load32(c, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = lds_f32x4(e.svec_s + (c + j) * 4);
+          const float4 b = lds_f32x4_ro(e.svec_s + (c + j) * 4);
           float y0 = v[j] + b.x, y1 = v[j + 1] + b.y, y2 = v[j + 2] + b.z, y3 = v[j + 3] + b.w;
           s += (y0 + y1) + (y2 + y3);
           ss += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
@@ -337,7 +350,7 @@ struct Epi2F32Img {
       if (kLn) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = lds_f32x4(e.svec_s + (c + j) * 4);
+          const float4 b = lds_f32x4_ro(e.svec_s + (c + j) * 4);
           v[j] = (v[j] + b.x - mean) * rstd; v[j + 1] = (v[j + 1] + b.y - mean) * rstd;
           v[j + 2] = (v[j + 2] + b.z - mean) * rstd; v[j + 3] = (v[j + 3] + b.w - mean) * rstd;
         }
@@ -346,8 +359,8 @@ struct Epi2F32Img {
       __syncwarp();
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kLn) {
-        g = lds_f32x4(e.svec_s + (512 + c + c4 * 4) * 4);
-        b = lds_f32x4(e.svec_s + (1024 + c + c4 * 4) * 4);
+        g = lds_f32x4_ro(e.svec_s + (512 + c + c4 * 4) * 4);
+        b = lds_f32x4_ro(e.svec_s + (1024 + c + c4 * 4) * 4);
       } else if (bias) {
         b = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
       }

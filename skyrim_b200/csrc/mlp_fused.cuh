@@ -57,7 +57,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
             const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
             const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg, int expflags) {
   using Cfg = MlpCfg<C>;
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define SKY_T(i, stmt) do { long long _t0 = dbg ? clock64() : 0; stmt; if (dbg) tacc[i] += clock64() - _t0; } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,6 +227,8 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
     uint32_t cnt = 0, tph = 0;
     constexpr int COLS_PER_WARP = Cfg::HC / 2;
     for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x, tph ^= 1) {
+      ctx.row0 = (long long)mt * 128 + q * 32;
+      epi.template prefetch<C>(ctx);  // residual rows -> L2 while the tile's GEMMs run
       for (int j = 0; j < Cfg::NCH; ++j, ++cnt) {
         const uint32_t buf = cnt & 1, use = cnt >> 1;
         SKY_T(0, mbar_wait(&acc1_full[buf], use & 1));
@@ -239,14 +241,14 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
 #pragma unroll
         for (int g = 0; g < COLS_PER_WARP / 32; ++g) {
           float v[32];
-          tmem_ld32(taddr + g * 32, v);
+          SKY_T(6, tmem_ld32(taddr + g * 32, v));
           const int hc = part * COLS_PER_WARP + g * 32;          // column inside the chunk
           const uint32_t bb = b1s_s + (j * Cfg::HC + hc) * 4;
 #pragma unroll
           if (!(expflags & 1)) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = lds_f32x4(bb + i * 4);
+            const float4 b4 = lds_f32x4_ro(bb + i * 4);
             gelu_erf_x2(v[i], v[i + 1], b4.x, b4.y);
             gelu_erf_x2(v[i + 2], v[i + 3], b4.z, b4.w);
           }
@@ -284,7 +286,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
     }
   }
   if (dbg && lane == 0 && (warp == 0 || warp == 9) && blockIdx.x < 4) {
-    for (int i = 0; i < 8; ++i) dbg[(blockIdx.x * 2 + (warp == 9)) * 8 + i] = tacc[i];
+    for (int i = 0; i < 16; ++i) dbg[(blockIdx.x * 2 + (warp == 9)) * 16 + i] = tacc[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -300,7 +302,7 @@ int launch_mlp_fused(const uint8_t* xh_in, const Epi2F32Img<true, true>& epi, co
                      const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
   static int dbg_runs = 0;
-  if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 64 * 8);
+  if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 256 * 8);
   using Cfg = MlpCfg<C>;
   auto kern = k_mlp_fused<C>;
   static bool configured = false;
@@ -316,10 +318,10 @@ int launch_mlp_fused(const uint8_t* xh_in, const Epi2F32Img<true, true>& epi, co
     ++dbg_runs;
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) {
-      const long long* e = dbg + (b * 2) * 8; const long long* m = dbg + (b * 2 + 1) * 8;
-      printf("[mlp C=%d cta %d, %d tiles/cta] EPI wait_acc1 %lld wait_hidempty %lld gelu %lld fence+arrive %lld wait_acc2 %lld ln %lld | "
+      const long long* e = dbg + (b * 2) * 16; const long long* m = dbg + (b * 2 + 1) * 16;
+      printf("[mlp C=%d cta %d, %d tiles/cta] EPI wait_acc1 %lld wait_hidempty %lld gelu %lld (ldtm %lld) fence+arrive %lld wait_acc2 %lld ln %lld | "
              "MMA wait_a %lld wait_acc1empty %lld wait_w1 %lld wait_hidfull %lld wait_w2 %lld\n", C, b, (tiles + grid - 1) / grid,
-             e[0], e[1], e[2], e[3], e[4], e[5], m[0], m[1], m[2], m[3], m[4]);
+             e[0], e[1], e[2], e[6], e[3], e[4], e[5], m[0], m[1], m[2], m[3], m[4]);
     }
   }
   SKY_CUDA_OK(cudaGetLastError());

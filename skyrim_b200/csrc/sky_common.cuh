@@ -132,6 +132,13 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+// read-only variant (bias / gamma / beta vectors that are written once before the role
+// dispatch): not volatile, so the compiler may batch and hoist these loads
+__device__ __forceinline__ float4 lds_f32x4_ro(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
