@@ -133,21 +133,33 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
   *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * tile_bytes + o) = *reinterpret_cast<uint4*>(l);
 }
 
-// per-column sums of (optionally GELU'd) fp32 [P, E]:  sums[c], sums[E + c]  (instance norm)
+// per-column sums of (optionally GELU'd) fp32 [P, E]:  sums[c], sums[E + c]  (instance norm).
+// Block = (32 column lanes) x (8 row lanes): each thread strides over its rows, the 8 partials
+// of a column meet in shared memory, one fp64 atomic per (block, column).
 __global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ x, long long P, int E, int act,
                                                   double* __restrict__ sums, int rows_per_block) {
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int i = 0; i < rows_per_block; ++i) {
+  __shared__ float red[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f, ss = 0.f;
+  if (c < E) {
+    for (int i = ry; i < rows_per_block; i += 8) {
       const long long r = r0 + i;
       if (r >= P) break;
       float v = x[r * E + c];
       if (act) v = gelu_erf(v);
       s += v; ss += v * v;
     }
-    atomicAdd(&sums[c], (double)s);
-    atomicAdd(&sums[E + c], (double)ss);
+  }
+  red[0][ry][cx] = s; red[1][ry][cx] = ss;
+  __syncthreads();
+  if (ry == 0 && c < E) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += red[0][i][cx]; b += red[1][i][cx]; }
+    atomicAdd(&sums[c], (double)a);
+    atomicAdd(&sums[E + c], (double)b);
   }
 }
 // sc = gamma * rstd, sh = beta - mean * sc
@@ -445,8 +457,9 @@ struct SfnoEngine : Engine {
   int norm_stats(const float* x, long long P, int act, const float* g, const float* b, cudaStream_t st) {
     prof_begin(KT_SFNO_MISC, st);
     SKY_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * E * sizeof(double), st));
-    const int rpb = 64;
-    k_colstats<<<(unsigned)((P + rpb - 1) / rpb), 256, 0, st>>>(x, P, E, act, sums, rpb);
+    const int rpb = 512;
+    dim3 grid((unsigned)((E + 31) / 32), (unsigned)((P + rpb - 1) / rpb));
+    k_colstats<<<grid, 256, 0, st>>>(x, P, E, act, sums, rpb);
     k_finalize_norm<<<(E + 127) / 128, 128, 0, st>>>(sums, g, b, cfg.eps, P, E, n_sc, n_sh);
     prof_end(KT_SFNO_MISC, st);
     count_launch(2);
