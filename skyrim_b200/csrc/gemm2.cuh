@@ -70,7 +70,8 @@ struct EpiCtx {
   int part, nparts; // column-chunk partition among the warps sharing a lane quarter
   float* patch;     // [32][33] floats, private to the warp
   uint32_t patch_s;    // the same patch as a shared-space address
-  uint32_t svec_s;     // shared-space address of bias[512] | gamma[512] | beta[512] (LN epilogues)
+  uint32_t svec_s;     // shared-space address of bias | gamma | beta, vstride floats apart (LN epilogues)
+  int vstride = 512;
 };
 
 struct AccTmem2 {
@@ -94,7 +95,9 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
   uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // warp index through a shuffle: provably warp-uniform, so the role branches are uniform control flow and the
+  // issuer's descriptor arithmetic runs on the uniform datapath (no per-MMA R2UR/ELECT waterfall)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   const int num_tiles = num_m_tiles * num_n_tiles;
   constexpr int LOADER = EPI_WARPS, MMAW = EPI_WARPS + 1;
 
@@ -142,20 +145,21 @@ k_gemm2(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long lo
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + G2_A_BYTES;
+          const uint64_t da = make_desc_sw128(a_addr);                 // +2 in the address field = +32 B = one K=16 step
+          const uint64_t db = make_desc_sw128(a_addr + G2_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_desc_sw128(a_addr + k * 32);
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int ni = 0; ni < Cfg::N_SPLIT; ++ni) {
-              const uint64_t db = make_desc_sw128(b_addr + ni * Cfg::N_INST * 128 + k * 32);
-              tc_mma_f16(d_tmem + ni * Cfg::N_INST, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int ni = 0; ni < Cfg::N_SPLIT; ++ni)
+                tc_mma_f16(d_tmem + ni * Cfg::N_INST, da + 2 * k, db + (uint64_t)(ni * Cfg::N_INST * 8 + 2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
             }
+            tc_commit(&empty[s]);
+            if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
           }
-          tc_commit(&empty[s]);
-          if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
         }
         __syncwarp();
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -359,8 +363,8 @@ struct Epi2F32Img {
       __syncwarp();
       float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kLn) {
-        g = lds_f32x4_ro(e.svec_s + (512 + c + c4 * 4) * 4);
-        b = lds_f32x4_ro(e.svec_s + (1024 + c + c4 * 4) * 4);
+        g = lds_f32x4_ro(e.svec_s + (e.vstride + c + c4 * 4) * 4);
+        b = lds_f32x4_ro(e.svec_s + (2 * e.vstride + c + c4 * 4) * 4);
       } else if (bias) {
         b = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
       }

@@ -51,7 +51,9 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
   uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // warp index through a shuffle: provably warp-uniform, so the role branches are uniform control flow and the
+  // issuer's descriptor arithmetic runs on the uniform datapath (no per-MMA R2UR/ELECT waterfall)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   const int tiles_per_batch = num_m_tiles * num_n_tiles;
   const long long num_tiles = (long long)tiles_per_batch * batches;
   constexpr int LOADER = EPI_WARPS, MMAW = EPI_WARPS + 1;
@@ -97,20 +99,21 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + G2_A_BYTES;
+          const uint64_t da = make_desc_sw128(a_addr);                 // +2 in the address field = +32 B = one K=16 step
+          const uint64_t db = make_desc_sw128(a_addr + G2_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_desc_sw128(a_addr + k * 32);
+            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int ni = 0; ni < Cfg::N_SPLIT; ++ni) {
-              const uint64_t db = make_desc_sw128(b_addr + ni * Cfg::N_INST * 128 + k * 32);
-              tc_mma_f16(d_tmem + ni * Cfg::N_INST, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int ni = 0; ni < Cfg::N_SPLIT; ++ni)
+                tc_mma_f16(d_tmem + ni * Cfg::N_INST, da + 2 * k, db + (uint64_t)(ni * Cfg::N_INST * 8 + 2 * k), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
             }
+            tc_commit(&empty[s]);
+            if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
           }
-          tc_commit(&empty[s]);
-          if (kb == num_kb - 1) tc_commit(&tmem_full[buf]);
         }
         __syncwarp();
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }

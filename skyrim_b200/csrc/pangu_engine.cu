@@ -19,6 +19,7 @@
 #include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
 #include "mlp_fused.cuh"
+#include "mlp_fused2.cuh"
 
 namespace sky {
 
@@ -126,6 +127,9 @@ struct PanguEngine : Engine {
   Geo g1, g2;
   int nch, nup;
   bool use_ref = false;
+  // fused MLP on CTA pairs (cta_group::2) per channel width; SKY_MLP=1cta|pair192|pair384 selects for A/B timing
+  bool mlp_pair192 = true, mlp_pair384 = true;
+  bool prof_split = false;  // SKY_PROF_SPLIT: report the C=384 MLP launches under the (otherwise unused) fc2 tag
   std::vector<void*> owned;
   GemmW embed_u, embed_s, down, up1, up2, rec;
   std::vector<BlockW> blocks[4];
@@ -150,6 +154,11 @@ struct PanguEngine : Engine {
     g2 = mk((H + 1) / 2, W / 2, 2 * c.dim, c.heads[1]);
     const char* e = getenv("SKY_GEMM");
     use_ref = e && !strcmp(e, "ref");
+    const char* m = getenv("SKY_MLP");
+    if (m && !strcmp(m, "1cta")) mlp_pair192 = mlp_pair384 = false;
+    if (m && !strcmp(m, "pair192")) mlp_pair384 = false;
+    if (m && !strcmp(m, "pair384")) mlp_pair192 = false;
+    prof_split = getenv("SKY_PROF_SPLIT") != nullptr;
   }
   ~PanguEngine() override {
     for (void* p : owned) cudaFree(p);
@@ -221,7 +230,8 @@ struct PanguEngine : Engine {
         if ((rc = pack(b.proj, N("proj.w"), c, c, c, false, st))) return rc;
         if ((rc = pack(b.fc1, N("fc1.w"), 4 * c, c, 192, false, st))) return rc;
         if ((rc = pack(b.fc2, N("fc2.w"), c, 4 * c, c, false, st))) return rc;
-        if ((rc = pack(b.fc1f, N("fc1.w"), 4 * c, c, c == 192 ? MlpCfg<192>::HC : MlpCfg<384>::HC, false, st))) return rc;
+        const int hc = (c == 192 ? mlp_pair192 : mlp_pair384) ? 128 : (c == 192 ? MlpCfg<192>::HC : MlpCfg<384>::HC);
+        if ((rc = pack(b.fc1f, N("fc1.w"), 4 * c, c, hc, false, st))) return rc;
         P(b.qkv_b, N("qkv.b"), 3 * c); P(b.proj_b, N("proj.b"), c);
         P(b.fc1_b, N("fc1.b"), 4 * c); P(b.fc2_b, N("fc2.b"), c);
         P(b.ln1_g, N("ln1.g"), c); P(b.ln1_b, N("ln1.b"), c);
@@ -345,11 +355,16 @@ struct PanguEngine : Engine {
     }
     if (!use_ref) {  // fused MLP: fc1 + GELU + fc2 + LayerNorm + residual, hidden stays on the SM
       Epi2F32Img<true, true> e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
-      prof_begin(KT_MLP, st);
+      const KTag tag = (prof_split && C == 384) ? KT_FC2 : KT_MLP;
+      prof_begin(tag, st);
       count_launch();
-      rc = C == 192 ? launch_mlp_fused<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
-                    : launch_mlp_fused<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
-      prof_end(KT_MLP, st);
+      if (C == 192)
+        rc = mlp_pair192 ? launch_mlp_fused_pair<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
+                         : launch_mlp_fused<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
+      else
+        rc = mlp_pair384 ? launch_mlp_fused_pair<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
+                         : launch_mlp_fused<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
+      prof_end(tag, st);
       if (rc) return rc;
     } else {  // two plain GEMMs through an HBM-resident hidden image (reference path only)
       AImage A{xh, xh, nkb, 0};
