@@ -19,8 +19,9 @@ namespace sky {
 
 constexpr int G2_BLOCK_M = 128;
 constexpr int G2_A_BYTES = G2_BLOCK_M * 128;
-constexpr int G2_PATCH_LD = 33;
-constexpr int G2_PATCH_FLOATS = 32 * G2_PATCH_LD;
+constexpr int G2_PATCH_LD = 33;    // scalar accessors (odd stride: conflict-free column reads)
+constexpr int G2_PATCHV_LD = 36;   // 128-bit accessors (row stride 144 B: conflict-free per quarter warp both ways)
+constexpr int G2_PATCH_FLOATS = 32 * G2_PATCHV_LD;
 
 // element (row, col) of an fp16 tile image with nkb k-blocks per row tile -> byte offset
 __device__ __forceinline__ size_t img_offset(long long row, int col, int nkb) {
@@ -230,6 +231,13 @@ __device__ __forceinline__ void patch_put_s(uint32_t patch_s, int lane, const fl
 #pragma unroll
   for (int j = 0; j < 32; ++j) sts_f32(a + 4 * j, v[j]);
 }
+// row-owner write of a 32x32 fp32 block with 128-bit stores (patch stride G2_PATCHV_LD)
+__device__ __forceinline__ void patch_put_v(uint32_t patch_s, int lane, const float (&v)[32]) {
+  const uint32_t a = patch_s + lane * (G2_PATCHV_LD * 4);
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 4 * j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+}
 // 8 consecutive floats of patch row rr starting at column c8 -> 8 halves
 __device__ __forceinline__ uint4 patch_get_h8(uint32_t patch_s, int rr, int c8) {
   const uint32_t a = patch_s + (rr * G2_PATCH_LD + c8) * 4;
@@ -300,6 +308,7 @@ struct Epi2F32Img {
   float* x; int ldx;            // fp32 row-major
   uint8_t* img; int nkb;        // fp16 image of the same rows (may be null)
   const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
+  int exp = 0;  // timing experiments only (results invalid): 1 = no residual loads, 2 = no fp32 stores, 4 = no image stores
   // Pull this warp's residual rows into L2 ahead of time.  A register-destination prefetch does
   // not work here: tcgen05.wait::ld also waits for the thread's outstanding global loads, so
   // every TMEM read in run() would expose the full HBM latency (profiles/r1_mlp.md).
@@ -312,93 +321,120 @@ struct Epi2F32Img {
 #pragma unroll
     for (int i = e.part; i < BN * 4 / 128; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
   }
+  // Per 32x32 block: the row-owner lanes drop the raw accumulator into the warp's patch with 128-bit
+  // stores, then every lane works on (row = it*4 + lane/8, 4 columns = lane%8) pieces: 8 lanes cover a
+  // full 128-byte row segment of x, so residual loads and stores are coalesced 128-bit accesses.  The
+  // LayerNorm statistics of the 8 rows a lane touches come from their owner lanes by shuffle; the
+  // fp16 image chunks (8 columns = 16 bytes) are assembled from lane pairs by shuffle, not through
+  // shared memory.  Every warp reduces the statistics of its own column groups only; the warps that
+  // share a lane quarter exchange partial sums through their patches.
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& e) const {
-    const int rsub4 = e.lane >> 3, c4 = e.lane & 7;   // fp32 phase
-    const int rsub8 = e.lane >> 2, ch = e.lane & 3;   // fp16 image phase
-    const int step = 32 * e.nparts;
+    constexpr int NG = BN / 32;
+    const int rsub4 = e.lane >> 3, c4 = e.lane & 7;
     const long long rows_left = e.M - e.row0;          // >= 32 for every tile but the last
     float* xp = x + e.row0 * ldx + e.n0 + c4 * 4;
-    // the residual rows are prefetched one column chunk ahead (the first chunk before the
-    // statistics pass): the epilogue is bound by the latency of these loads
+    const bool ld_on = kResidual && !(exp & 1);
     float4 xin[8];
-    if (kResidual) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rsub4;
-        xin[it] = (rr < rows_left && e.part * 32 < BN) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + rsub4;
+      xin[it] = (ld_on && rr < rows_left && e.part < NG) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
     }
-    float mean = 0.f, rstd = 1.f;
+    float rs[8], ns[8];   // rstd and -mean*rstd of row it*4 + rsub4
+#pragma unroll
+    for (int it = 0; it < 8; ++it) { rs[it] = 1.f; ns[it] = 0.f; }
     if (kLn) {
       float s = 0.f, ss = 0.f;
-      for (int c = 0; c < BN; c += 32) {
+      for (int g = e.part; g < NG; g += e.nparts) {
         float v[32];
-        acc.load32(c, v);
+        acc.load32(g * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b = lds_f32x4_ro(e.svec_s + (c + j) * 4);
-          float y0 = v[j] + b.x, y1 = v[j + 1] + b.y, y2 = v[j + 2] + b.z, y3 = v[j + 3] + b.w;
+          const float4 b = lds_f32x4_ro(e.svec_s + (g * 32 + j) * 4);
+          const float y0 = v[j] + b.x, y1 = v[j + 1] + b.y, y2 = v[j + 2] + b.z, y3 = v[j + 3] + b.w;
           s += (y0 + y1) + (y2 + y3);
           ss += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
         }
       }
-      mean = s / BN;
-      rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+      if (e.nparts > 1) {
+        const uint32_t slot = e.patch_s + e.lane * 8;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(s), "f"(ss) : "memory");
+        const int q = (int)((e.row0 >> 5) & 3);
+        asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(32 * e.nparts) : "memory");
+        for (int p = 0; p < e.nparts; ++p) {
+          if (p == e.part) continue;
+          float ps, pss;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(slot + (p - e.part) * 4 * G2_PATCH_FLOATS * 4));
+          s += ps; ss += pss;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(32 * e.nparts) : "memory");   // the patches are reused below
+      }
+      const float mean = s / BN;
+      const float rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+      const float nmr = -mean * rstd;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        rs[it] = __shfl_sync(0xffffffffu, rstd, it * 4 + rsub4);
+        ns[it] = __shfl_sync(0xffffffffu, nmr, it * 4 + rsub4);
+      }
     }
     const uint32_t r0 = (uint32_t)(e.row0 & 127);
-    for (int c = e.part * 32; c < BN; c += step) {
-      float v[32];
-      acc.load32(c, v);
-      if (kLn) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = lds_f32x4_ro(e.svec_s + (c + j) * 4);
-          v[j] = (v[j] + b.x - mean) * rstd; v[j + 1] = (v[j + 1] + b.y - mean) * rstd;
-          v[j + 2] = (v[j + 2] + b.z - mean) * rstd; v[j + 3] = (v[j + 3] + b.w - mean) * rstd;
-        }
+    const int odd = e.lane & 1;
+    for (int g = e.part; g < NG; g += e.nparts) {
+      const int c = g * 32;
+      {
+        float v[32];
+        acc.load32(c, v);
+        patch_put_v(e.patch_s, e.lane, v);
       }
-      patch_put_s(e.patch_s, e.lane, v);
       __syncwarp();
-      float4 g = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f), ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
       if (kLn) {
-        g = lds_f32x4_ro(e.svec_s + (e.vstride + c + c4 * 4) * 4);
-        b = lds_f32x4_ro(e.svec_s + (2 * e.vstride + c + c4 * 4) * 4);
+        bs = lds_f32x4_ro(e.svec_s + (c + c4 * 4) * 4);
+        ga = lds_f32x4_ro(e.svec_s + (e.vstride + c + c4 * 4) * 4);
+        be = lds_f32x4_ro(e.svec_s + (2 * e.vstride + c + c4 * 4) * 4);
       } else if (bias) {
-        b = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
+        bs = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
       }
+      const bool more = g + e.nparts < NG;
       float4 xnext[8];
       if (kResidual) {
-        const bool more = c + step < BN;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + rsub4;
-          xnext[it] = (more && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c + step)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          xnext[it] = (more && ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c + 32 * e.nparts)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      const int col = e.n0 + c;
+      uint8_t* ibase = img ? img + ((size_t)(e.row0 >> 7) * nkb + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128 : nullptr;
+      const uint32_t cb = (((uint32_t)col & 63u) >> 3) + (uint32_t)(c4 >> 1);   // 16-byte chunk of this lane pair inside the image row
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rsub4;
-        const uint32_t pa = e.patch_s + (rr * G2_PATCH_LD + c4 * 4) * 4;
-        float4 y;
-        y.x = lds_f32(pa) * g.x + b.x; y.y = lds_f32(pa + 4) * g.y + b.y;
-        y.z = lds_f32(pa + 8) * g.z + b.z; y.w = lds_f32(pa + 12) * g.w + b.w;
-        if (kResidual) { y.x += xin[it].x; y.y += xin[it].y; y.z += xin[it].z; y.w += xin[it].w; }
-        if (rr < rows_left) *reinterpret_cast<float4*>(xp + (size_t)rr * ldx + c) = y;
-        sts_f32(pa, y.x); sts_f32(pa + 4, y.y); sts_f32(pa + 8, y.z); sts_f32(pa + 12, y.w);
-      }
-      __syncwarp();
-      if (img) {
-        const int col = e.n0 + c;
-        uint8_t* ibase = img + ((size_t)(e.row0 >> 7) * nkb + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
+      for (int it2 = 0; it2 < 8; it2 += 2) {
+        uint2 h[2];
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + rsub8;
-          const uint4 pk = patch_get_h8(e.patch_s, rr, ch * 8);
-          if (rr < rows_left)
-            *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
+        for (int u = 0; u < 2; ++u) {
+          const int it = it2 + u;
+          const int rr = it * 4 + rsub4;
+          const float4 t = lds_f32x4(e.patch_s + (rr * G2_PATCHV_LD + c4 * 4) * 4);
+          float4 y;
+          y.x = fmaf(fmaf(t.x + bs.x, rs[it], ns[it]), ga.x, be.x); y.y = fmaf(fmaf(t.y + bs.y, rs[it], ns[it]), ga.y, be.y);
+          y.z = fmaf(fmaf(t.z + bs.z, rs[it], ns[it]), ga.z, be.z); y.w = fmaf(fmaf(t.w + bs.w, rs[it], ns[it]), ga.w, be.w);
+          if (kResidual) { y.x += xin[it].x; y.y += xin[it].y; y.z += xin[it].z; y.w += xin[it].w; }
+          if (rr < rows_left && !(exp & 2)) *reinterpret_cast<float4*>(xp + (size_t)rr * ldx + c) = y;
+          h[u].x = pack_half2(y.x, y.y); h[u].y = pack_half2(y.z, y.w);
+        }
+        if (ibase && !(exp & 4)) {
+          // even lane assembles the chunk of row it2, odd lane the chunk of row it2+1: swap the other halves
+          const uint2 send = odd ? h[0] : h[1];
+          uint2 recv;
+          recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+          recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+          const int rr = (it2 + odd) * 4 + rsub4;
+          const uint4 pk = odd ? make_uint4(recv.x, recv.y, h[1].x, h[1].y) : make_uint4(h[0].x, h[0].y, recv.x, recv.y);
+          if (rr < rows_left) *reinterpret_cast<uint4*>(ibase + rr * 128 + ((cb ^ (uint32_t)(rr & 7)) << 4)) = pk;
         }
       }
       __syncwarp();
@@ -409,6 +445,9 @@ struct Epi2F32Img {
     }
   }
 };
+
+// post-norm residual of the attention projection and of the MLP
+using EpiLnRes = Epi2F32Img<true, true>;
 
 // up-sample linear1 (N = 4C as (hs, ws, C); one n-tile = one sub-position): LayerNorm over
 // the C features of the tile, written as fp16 image rows of the FINE token

@@ -52,7 +52,7 @@ struct MlpCfg {
 template <int C>
 __global__ void __launch_bounds__(352, 1)
 k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
-            const Epi2F32Img<true, true> epi,   // x (fp32), xh out image, b2, gamma, beta
+            const EpiLnRes epi,   // x (fp32), xh out image, b2, gamma, beta
             const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
             const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
             const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg, int expflags) {
@@ -298,7 +298,7 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
 }
 
 template <int C>
-int launch_mlp_fused(const uint8_t* xh_in, const Epi2F32Img<true, true>& epi, const uint8_t* W1img,
+int launch_mlp_fused(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W1img,
                      const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
   static int dbg_runs = 0;

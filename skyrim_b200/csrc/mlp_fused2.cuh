@@ -9,12 +9,11 @@
 // core are halved per SM.  At C=384 the single-CTA kernel is shared-memory-bandwidth bound
 // (DESIGN.md §7); this is the fix.
 //
-// Per CTA, 352 threads: warps 0..7 epilogue (GELU per chunk, LayerNorm + residual per tile),
-// 8 loader (A tile + W1 ring), 9 MMA issuer in the even CTA / completion relay in the odd CTA,
-// 10 loader (W2 ring).  1-D bulk copies cannot signal an mbarrier of the peer CTA, so the odd
-// CTA's warp 9 forwards "my operand landed" to the issuer with remote mbarrier arrives, in the
-// issuer's own consumption order.  tcgen05.commit multicasts "operands consumed / accumulator
-// ready" to both CTAs.
+// Per CTA, 320 threads: warps 0..7 epilogue (GELU per chunk, LayerNorm + residual per tile),
+// 8 loader (A tile + the weight ring), 9 MMA issuer in the even CTA / completion relay in the odd
+// CTA.  1-D bulk copies cannot signal an mbarrier of the peer CTA, so the odd CTA's warp 9 forwards
+// "my operand landed" to the issuer with remote mbarrier arrives, in the issuer's own consumption
+// order.  tcgen05.commit multicasts "operands consumed / accumulator ready" to both CTAs.
 //
 //   TMEM columns (per CTA): acc1[ACC1_BUFS] (HC=128 each) | acc2 (C)
 //     C=192: 2*128 + 192 = 448      C=384: 128 + 384 = 512 (acc1 single buffered: the epilogue
@@ -33,66 +32,63 @@ struct Mlp2Cfg {
   static constexpr int HC = 128;
   static constexpr int NCH = 4 * C / HC;
   static constexpr int HKB = HC / 64;
-  static constexpr int NH = C / 192;
   static constexpr int ACC1_BUFS = (2 * HC + C <= 512) ? 2 : 1;
   static constexpr int W1_FULL = HC * 128;       // one (chunk, k-block) item of the W1 image
   static constexpr int W1_HALF = W1_FULL / 2;    // this CTA's 64 rows of it
-  static constexpr int W2_HALF = 96 * 128;       // this CTA's 96 of the 192 rows of a W2 item
-  static constexpr int S1 = C == 192 ? 6 : 4;
-  static constexpr int S2 = C == 192 ? 4 : 2;
+  // GEMM2 runs as NP MMAs of N2 output columns per K=16 step.  C=384 uses N2=128 so that a W2 item is
+  // 8 KB like a W1 item and both share ONE ring in consumption order: with separate rings the idle
+  // ring's slots hold nothing while the other one starves (measured: the issuer waited 2k cycles per
+  // chunk on W2 with 2 slots, profiles/r1_mlp_pair.md).
+  static constexpr int N2 = C == 384 ? 128 : 192;
+  static constexpr int NP = C / N2;
+  static constexpr int W2_HALF = N2 / 2 * 128;   // this CTA's N2/2 rows of a (k-block, n-part) item of the W2 image
+  static constexpr int SLOT = W1_HALF > W2_HALF ? W1_HALF : W2_HALF;
+  static constexpr int S = C == 192 ? 8 : 7;
   static constexpr int A_BYTES = NKB * G2_A_BYTES;
   static constexpr int HID_BYTES = HKB * G2_A_BYTES;
-  static constexpr int OFF_W1 = A_BYTES;
-  static constexpr int OFF_W2 = OFF_W1 + S1 * W1_HALF;
-  static constexpr int OFF_HID = OFF_W2 + S2 * W2_HALF;
+  static constexpr int OFF_W = A_BYTES;
+  static constexpr int OFF_HID = OFF_W + S * SLOT;
   static constexpr int PATCH_BYTES = 8 * G2_PATCH_FLOATS * 4;   // LN patches alias the hidden buffers
   static constexpr int HID_REGION = 2 * HID_BYTES;
   static constexpr int OFF_VEC = OFF_HID + HID_REGION;          // b1[4C]
   static constexpr int OFF_LNV = OFF_VEC + 4 * C * 4;           // bias2 | gamma | beta, C floats apart
   static constexpr int OFF_BAR = OFF_LNV + 3 * C * 4;
-  static constexpr int NBARS = 3 + 3 * S1 + 3 * S2 + 8 + 2;
+  static constexpr int NBARS = 3 + 3 * S + 8 + 2;
   static constexpr int SMEM_BYTES = OFF_BAR + (NBARS * 8 + 8 + 15) / 16 * 16;
   static constexpr int ACC2_COL = ACC1_BUFS * HC;
-  static constexpr int THREADS = 352;
+  static constexpr int THREADS = 320;
   static_assert(ACC1_BUFS * HC + C <= 512, "TMEM budget");
   static_assert(HID_REGION >= PATCH_BYTES, "LN patches must fit in the hidden buffers");
+  static_assert(SLOT % 1024 == 0, "operand slots must keep the 1024-byte swizzle atom alignment");
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
 template <int C>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(352, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
-                 const Epi2F32Img<true, true> epi,   // x (fp32), xh out image, b2, gamma, beta
+                 const EpiLnRes epi,   // x (fp32), xh out image, b2, gamma, beta
                  const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
                  const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
-                 const float* __restrict__ b1, long long M, int num_m_tiles, int expflags, long long* dbg) {
+                 const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg) {
   using Cfg = Mlp2Cfg<C>;
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define SKY_T2(i, stmt) do { long long _t0 = dbg ? clock64() : 0; stmt; if (dbg) tacc[i] += clock64() - _t0; } while (0)
   const long long t_begin = dbg ? clock64() : 0;
-  // waits are CTA-scope acquires: a cluster-scope acquire adds CCTL.IVALL (L1 invalidate) after every wait and no
-  // thread here reads peer-written memory through the generic proxy.  expflags bit1 (timing experiment) = cluster-scope waits
-  auto waitc = [&](uint64_t* bar, uint32_t par) { if (expflags & 2) mbar_wait_cluster(bar, par); else mbar_wait(bar, par); };
-  auto waitp = [&](uint64_t* bar, uint32_t par) { if (expflags & 2) mbar_wait_cluster(bar, par); else mbar_wait(bar, par); };
   extern __shared__ __align__(1024) uint8_t smem_pair[];
   uint8_t* smem = smem_pair;
   uint8_t* a_s = smem;
-  uint8_t* w1_s = smem + Cfg::OFF_W1;
-  uint8_t* w2_s = smem + Cfg::OFF_W2;
+  uint8_t* w_s = smem + Cfg::OFF_W;
   uint8_t* hid_s = smem + Cfg::OFF_HID;
   float* b1s = reinterpret_cast<float*>(smem + Cfg::OFF_VEC);
   float* lnv = reinterpret_cast<float*>(smem + Cfg::OFF_LNV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* a_peer = bars + 2;
-  uint64_t* w1_full = bars + 3;                 // [S1]
-  uint64_t* w1_empty = w1_full + Cfg::S1;       // [S1]
-  uint64_t* w1_peer = w1_empty + Cfg::S1;       // [S1]  (used in the even CTA)
-  uint64_t* w2_full = w1_peer + Cfg::S1;        // [S2]
-  uint64_t* w2_empty = w2_full + Cfg::S2;       // [S2]
-  uint64_t* w2_peer = w2_empty + Cfg::S2;       // [S2]  (used in the even CTA)
-  uint64_t* acc1_full = w2_peer + Cfg::S2;      // [2]
+  uint64_t* a_peer = bars + 2;                  //       (used in the even CTA)
+  uint64_t* w_full = bars + 3;                  // [S]
+  uint64_t* w_empty = w_full + Cfg::S;          // [S]
+  uint64_t* w_peer = w_empty + Cfg::S;          // [S]   (used in the even CTA)
+  uint64_t* acc1_full = w_peer + Cfg::S;        // [2]
   uint64_t* acc1_empty = acc1_full + 2;         // [2]   (even CTA, 16 arrivals)
   uint64_t* hid_full = acc1_empty + 2;          // [2]   (even CTA, 16 arrivals)
   uint64_t* hid_empty = hid_full + 2;           // [2]
@@ -110,8 +106,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(a_peer, 1);
-    for (int s = 0; s < Cfg::S1; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); mbar_init(&w1_peer[s], 1); }
-    for (int s = 0; s < Cfg::S2; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); mbar_init(&w2_peer[s], 1); }
+    for (int s = 0; s < Cfg::S; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&w_peer[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc1_full[b], 1); mbar_init(&acc1_empty[b], 16);
       mbar_init(&hid_full[b], 16); mbar_init(&hid_empty[b], 1);
@@ -128,13 +123,32 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Weight items travel through one ring in the order the issuer consumes them:
+  //   per tile:  W1(0) | W1(1) W2(0) | W1(2) W2(1) | ... | W1(NCH-1) W2(NCH-2) | W2(NCH-1)
+  // W1(j) = NKB items (k-blocks of chunk j), W2(j) = HKB*NP items (k-block, n-part).  Waits are CTA-scope
+  // acquires: a cluster-scope acquire adds CCTL.IVALL after every wait and no thread here reads
+  // peer-written memory through the generic proxy.
   if (warp == 8) {
-    // ===================== loader: own A tile + own half of the W1 ring =====================
+    // ===================== loader: own A tile + own half of every weight item =====================
     int s = 0; uint32_t ph = 0; uint32_t tph = 0;
+    auto put = [&](const uint8_t* src, uint32_t bytes) {
+      mbar_wait(&w_empty[s], ph ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&w_full[s], bytes);
+        bulk_g2s(w_s + s * Cfg::SLOT, src, bytes, &w_full[s]);
+      }
+      __syncwarp();
+      if (++s == Cfg::S) { s = 0; ph ^= 1; }
+    };
+    auto put_w2 = [&](int j) {
+      for (int kb2 = 0; kb2 < Cfg::HKB; ++kb2)
+        for (int np = 0; np < Cfg::NP; ++np)
+          put(W2img + ((size_t)(j * Cfg::HKB + kb2) * C + np * Cfg::N2 + rank * (Cfg::N2 / 2)) * 128, Cfg::W2_HALF);
+    };
     for (int sup = pair; sup < num_super; sup += npairs, tph ^= 1) {
       int mt = 2 * sup + (int)rank;
       if (mt > num_m_tiles - 1) mt = num_m_tiles - 1;   // odd tile count: the idle half recomputes the last tile, stores nothing
-      waitc(a_empty, tph ^ 1);
+      mbar_wait(a_empty, tph ^ 1);
       if (lane == 0) {
         mbar_arrive_expect_tx(a_full, Cfg::A_BYTES);
         for (int kb = 0; kb < Cfg::NKB; ++kb)
@@ -142,143 +156,88 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
       }
       __syncwarp();
       for (int j = 0; j < Cfg::NCH; ++j) {
-        for (int kb = 0; kb < Cfg::NKB; ++kb) {
-          waitc(&w1_empty[s], ph ^ 1);
-          if (lane == 0) {
-            mbar_arrive_expect_tx(&w1_full[s], Cfg::W1_HALF);
-            bulk_g2s(w1_s + s * Cfg::W1_HALF,
-                     W1img + ((size_t)j * Cfg::NKB + kb) * Cfg::W1_FULL + rank * Cfg::W1_HALF, Cfg::W1_HALF, &w1_full[s]);
-          }
-          __syncwarp();
-          if (++s == Cfg::S1) { s = 0; ph ^= 1; }
-        }
+        for (int kb = 0; kb < Cfg::NKB; ++kb)
+          put(W1img + ((size_t)j * Cfg::NKB + kb) * Cfg::W1_FULL + rank * Cfg::W1_HALF, Cfg::W1_HALF);
+        if (j >= 1) put_w2(j - 1);
       }
-    }
-  } else if (warp == 10) {
-    // ===================== loader: own half of the W2 ring =====================
-    int s = 0; uint32_t ph = 0;
-    for (int sup = pair; sup < num_super; sup += npairs) {
-      for (int j = 0; j < Cfg::NCH; ++j) {
-        for (int kb2 = 0; kb2 < Cfg::HKB; ++kb2) {
-          for (int nh = 0; nh < Cfg::NH; ++nh) {
-            waitc(&w2_empty[s], ph ^ 1);
-            if (lane == 0) {
-              mbar_arrive_expect_tx(&w2_full[s], Cfg::W2_HALF);
-              bulk_g2s(w2_s + s * Cfg::W2_HALF,
-                       W2img + ((size_t)(j * Cfg::HKB + kb2) * C + nh * 192 + rank * 96) * 128, Cfg::W2_HALF, &w2_full[s]);
-            }
-            __syncwarp();
-            if (++s == Cfg::S2) { s = 0; ph ^= 1; }
-          }
-        }
-      }
+      put_w2(Cfg::NCH - 1);
     }
   } else if (warp == 9 && rank == 0) {
     // ===================== MMA issuer (even CTA) =====================
     constexpr uint32_t idesc1 = make_idesc_f16(256, Cfg::HC);
-    constexpr uint32_t idesc2 = make_idesc_f16(256, 192);
-    int s1 = 0; uint32_t ph1 = 0; int s2 = 0; uint32_t ph2 = 0;
+    constexpr uint32_t idesc2 = make_idesc_f16(256, Cfg::N2);
+    int s = 0; uint32_t ph = 0;
     uint32_t tph = 0;        // tile parity (a_full, acc2)
     uint32_t cnt = 0;        // global chunk counter
     const uint32_t a_addr = smem_u32(a_s);
     const uint32_t hid_addr = smem_u32(hid_s);
-    auto gemm2 = [&](uint32_t ci /*global chunk id*/, bool first_of_tile) {
-      const uint32_t hb = ci & 1, use = ci >> 1;
-      SKY_T2(4, waitc(&hid_full[hb], use & 1));
-      if (first_of_tile) SKY_T2(7, waitc(acc2_empty, tph ^ 1));
+    const uint32_t w_addr = smem_u32(w_s);
+    // one weight item = 4 MMAs (K = 64); descriptors are computed by the whole warp (uniform datapath);
+    // +2 in the descriptor's address field = +32 bytes = one K=16 step
+    auto item = [&](uint32_t a_bytes, uint32_t d_tmem, uint32_t idesc, uint32_t acc0, uint64_t* extra0, uint64_t* extra1) {
+      SKY_T2(2, mbar_wait(&w_full[s], ph));
+      SKY_T2(3, mbar_wait(&w_peer[s], ph));
       tc_fence_after();
-      for (int kb2 = 0; kb2 < Cfg::HKB; ++kb2) {
-        for (int nh = 0; nh < Cfg::NH; ++nh) {
-          SKY_T2(5, mbar_wait(&w2_full[s2], ph2));
-          SKY_T2(6, waitp(&w2_peer[s2], ph2));
-          tc_fence_after();
-          {
-            // descriptors are computed by the whole warp (uniform); +2 in the address field = +32 bytes = one K=16 step
-            const uint64_t da = make_desc_sw128(hid_addr + hb * Cfg::HID_BYTES + kb2 * G2_A_BYTES);
-            const uint64_t db = make_desc_sw128(smem_u32(w2_s + s2 * Cfg::W2_HALF));
-            const uint32_t d_tmem = tmem_base + Cfg::ACC2_COL + nh * 192;
-            const uint32_t acc0 = (!first_of_tile || kb2 > 0) ? 1u : 0u;
-            if (elect_one()) {
-              tc_mma_f16_pair(d_tmem, da, db, idesc2, acc0);
-              tc_mma_f16_pair(d_tmem, da + 2, db + 2, idesc2, 1u);
-              tc_mma_f16_pair(d_tmem, da + 4, db + 4, idesc2, 1u);
-              tc_mma_f16_pair(d_tmem, da + 6, db + 6, idesc2, 1u);
-              tc_commit_pair(&w2_empty[s2]);
-            }
-          }
-          __syncwarp();
-          if (++s2 == Cfg::S2) { s2 = 0; ph2 ^= 1; }
-        }
+      const uint64_t da = make_desc_sw128(a_bytes);
+      const uint64_t db = make_desc_sw128(w_addr + s * Cfg::SLOT);
+      if (elect_one()) {
+        tc_mma_f16_pair(d_tmem, da, db, idesc, acc0);
+        tc_mma_f16_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+        tc_mma_f16_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+        tc_mma_f16_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+        tc_commit_pair(&w_empty[s]);
+        if (extra0) tc_commit_pair(extra0);
+        if (extra1) tc_commit_pair(extra1);
       }
-      if (elect_one()) tc_commit_pair(&hid_empty[hb]);
       __syncwarp();
+      if (++s == Cfg::S) { s = 0; ph ^= 1; }
+    };
+    auto gemm2 = [&](uint32_t ci /*global chunk id*/, bool first_of_tile, bool last_of_tile) {
+      const uint32_t hb = ci & 1, use = ci >> 1;
+      SKY_T2(4, mbar_wait(&hid_full[hb], use & 1));
+      if (first_of_tile) SKY_T2(7, mbar_wait(acc2_empty, tph ^ 1));
+      tc_fence_after();
+      for (int kb2 = 0; kb2 < Cfg::HKB; ++kb2)
+        for (int np = 0; np < Cfg::NP; ++np) {
+          const bool last = kb2 == Cfg::HKB - 1 && np == Cfg::NP - 1;
+          item(hid_addr + hb * Cfg::HID_BYTES + kb2 * G2_A_BYTES, tmem_base + Cfg::ACC2_COL + np * Cfg::N2, idesc2,
+               (!first_of_tile || kb2 > 0) ? 1u : 0u, last ? &hid_empty[hb] : nullptr, (last && last_of_tile) ? acc2_full : nullptr);
+        }
     };
     for (int sup = pair; sup < num_super; sup += npairs, tph ^= 1) {
       SKY_T2(0, mbar_wait(a_full, tph));
-      SKY_T2(0, waitp(a_peer, tph));
+      SKY_T2(0, mbar_wait(a_peer, tph));
       tc_fence_after();
       for (int j = 0; j < Cfg::NCH; ++j, ++cnt) {
         const uint32_t ab = cnt % Cfg::ACC1_BUFS, use = cnt / Cfg::ACC1_BUFS;
-        SKY_T2(1, waitc(&acc1_empty[ab], (use & 1) ^ 1));
+        SKY_T2(1, mbar_wait(&acc1_empty[ab], (use & 1) ^ 1));
         tc_fence_after();
         for (int kb = 0; kb < Cfg::NKB; ++kb) {
-          SKY_T2(2, mbar_wait(&w1_full[s1], ph1));
-          SKY_T2(3, waitp(&w1_peer[s1], ph1));
-          tc_fence_after();
-          {
-            const uint64_t da = make_desc_sw128(a_addr + kb * G2_A_BYTES);
-            const uint64_t db = make_desc_sw128(smem_u32(w1_s + s1 * Cfg::W1_HALF));
-            const uint32_t d_tmem = tmem_base + ab * Cfg::HC;
-            if (elect_one()) {
-              tc_mma_f16_pair(d_tmem, da, db, idesc1, kb != 0 ? 1u : 0u);
-              tc_mma_f16_pair(d_tmem, da + 2, db + 2, idesc1, 1u);
-              tc_mma_f16_pair(d_tmem, da + 4, db + 4, idesc1, 1u);
-              tc_mma_f16_pair(d_tmem, da + 6, db + 6, idesc1, 1u);
-              tc_commit_pair(&w1_empty[s1]);
-              if (kb == Cfg::NKB - 1) {
-                tc_commit_pair(&acc1_full[ab]);
-                if (j == Cfg::NCH - 1) tc_commit_pair(a_empty);
-              }
-            }
-          }
-          __syncwarp();
-          if (++s1 == Cfg::S1) { s1 = 0; ph1 ^= 1; }
+          const bool last = kb == Cfg::NKB - 1;
+          item(a_addr + kb * G2_A_BYTES, tmem_base + ab * Cfg::HC, idesc1, kb != 0 ? 1u : 0u, last ? &acc1_full[ab] : nullptr,
+               (last && j == Cfg::NCH - 1) ? a_empty : nullptr);
         }
-        if (j >= 1) gemm2(cnt - 1, j == 1);
+        if (j >= 1) gemm2(cnt - 1, j == 1, false);
       }
-      gemm2(cnt - 1, Cfg::NCH == 1);
-      if (elect_one()) tc_commit_pair(acc2_full);
-      __syncwarp();
+      gemm2(cnt - 1, Cfg::NCH == 1, true);
     }
   } else if (warp == 9) {
     // ===================== completion relay (odd CTA) =====================
-    // forwards "my half of the operand is in shared memory" to the issuer, in its consumption order
+    // 1-D bulk copies cannot signal the peer's mbarrier: forward "my half of the operand is in shared memory" to the issuer
     const uint32_t r_a = mapa_u32(smem_u32(a_peer), 0);
-    const uint32_t r_w1 = mapa_u32(smem_u32(w1_peer), 0);
-    const uint32_t r_w2 = mapa_u32(smem_u32(w2_peer), 0);
-    int s1 = 0; uint32_t ph1 = 0; int s2 = 0; uint32_t ph2 = 0; uint32_t tph = 0;
-    auto relay2 = [&]() {
-      for (int i = 0; i < Cfg::HKB * Cfg::NH; ++i) {
-        mbar_wait(&w2_full[s2], ph2);
-        if (lane == 0) mbar_arrive_cluster(r_w2 + s2 * 8);
-        __syncwarp();
-        if (++s2 == Cfg::S2) { s2 = 0; ph2 ^= 1; }
-      }
-    };
+    const uint32_t r_w = mapa_u32(smem_u32(w_peer), 0);
+    int s = 0; uint32_t ph = 0, tph = 0;
+    constexpr int ITEMS_PER_TILE = Cfg::NCH * (Cfg::NKB + Cfg::HKB * Cfg::NP);
     for (int sup = pair; sup < num_super; sup += npairs, tph ^= 1) {
       mbar_wait(a_full, tph);
       if (lane == 0) mbar_arrive_cluster(r_a);
       __syncwarp();
-      for (int j = 0; j < Cfg::NCH; ++j) {
-        for (int kb = 0; kb < Cfg::NKB; ++kb) {
-          mbar_wait(&w1_full[s1], ph1);
-          if (lane == 0) mbar_arrive_cluster(r_w1 + s1 * 8);
-          __syncwarp();
-          if (++s1 == Cfg::S1) { s1 = 0; ph1 ^= 1; }
-        }
-        if (j >= 1) relay2();
+      for (int i = 0; i < ITEMS_PER_TILE; ++i) {
+        mbar_wait(&w_full[s], ph);
+        if (lane == 0) mbar_arrive_cluster(r_w + s * 8);
+        __syncwarp();
+        if (++s == Cfg::S) { s = 0; ph ^= 1; }
       }
-      relay2();
     }
   } else {
     // ===================== epilogue warps 0..7 =====================
@@ -302,7 +261,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
       for (int j = 0; j < Cfg::NCH; ++j, ++cnt) {
         const uint32_t ab = cnt % Cfg::ACC1_BUFS, ause = cnt / Cfg::ACC1_BUFS;
         const uint32_t hb = cnt & 1, huse = cnt >> 1;
-        SKY_T2(0, waitc(&acc1_full[ab], ause & 1));
+        SKY_T2(0, mbar_wait(&acc1_full[ab], ause & 1));
         tc_fence_after();
         const long long _tg = dbg ? clock64() : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * Cfg::HC + part * 64;
@@ -314,7 +273,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(r_acc1_empty + ab * 8);   // accumulator is in registers: GEMM1 of the next chunk may start
-        SKY_T2(1, waitc(&hid_empty[hb], (huse & 1) ^ 1));
+        SKY_T2(1, mbar_wait(&hid_empty[hb], (huse & 1) ^ 1));
         uint8_t* kbase = hid_s + hb * Cfg::HID_BYTES + part * G2_A_BYTES;   // this warp's 64 columns = k-block `part` of the chunk
         const uint32_t bb = b1s_s + (j * Cfg::HC + part * 64) * 4;
 #pragma unroll
@@ -349,7 +308,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
         if (dbg) tacc[2] += clock64() - _tg;
       }
       // ---- LayerNorm + residual on the finished acc2 tile ----
-      SKY_T2(3, waitc(acc2_full, tph));
+      SKY_T2(3, mbar_wait(acc2_full, tph));
       tc_fence_after();
       const long long _tl = dbg ? clock64() : 0;
       AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::ACC2_COL};
@@ -377,7 +336,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
 }
 
 template <int C>
-int launch_mlp_fused_pair(const uint8_t* xh_in, const Epi2F32Img<true, true>& epi, const uint8_t* W1img,
+int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W1img,
                           const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
   static int dbg_runs = 0;
@@ -392,16 +351,15 @@ int launch_mlp_fused_pair(const uint8_t* xh_in, const Epi2F32Img<true, true>& ep
   const int tiles = (int)((M + 127) / 128);
   const int supers = (tiles + 1) / 2;
   const int pairs = supers < num_sms / 2 ? supers : num_sms / 2;
-  static const int expflags = getenv("SKY_MLP_EXP") ? atoi(getenv("SKY_MLP_EXP")) : 0;  // timing experiments only
-  kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(xh_in, epi, W1img, W2img, b1, M, tiles, expflags, dbg);
+  kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(xh_in, epi, W1img, W2img, b1, M, tiles, dbg);
   if (dbg && dbg_runs < 2) {
     ++dbg_runs;
     cudaDeviceSynchronize();
     for (int b = 0; b < 2; ++b) {   // CTA 0 = issuer, CTA 1 = its peer
       const long long* e = dbg + (b * 2) * 16; const long long* m = dbg + (b * 2 + 1) * 16;
       printf("[mlp-pair C=%d cta %d, %d supertiles/pair, total %lld] EPI wait_acc1 %lld wait_hidempty %lld gelu(incl) %lld wait_acc2 %lld ln %lld | "
-             "W9 wait_a %lld acc1empty %lld w1 %lld w1peer %lld hidfull %lld w2 %lld w2peer %lld acc2empty %lld\n", C, b,
-             (supers + pairs - 1) / pairs, e[15], e[0], e[1], e[2], e[3], e[4], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+             "W9 wait_a %lld acc1empty %lld w %lld wpeer %lld hidfull %lld acc2empty %lld\n", C, b,
+             (supers + pairs - 1) / pairs, e[15], e[0], e[1], e[2], e[3], e[4], m[0], m[1], m[2], m[3], m[4], m[7]);
     }
   }
   SKY_CUDA_OK(cudaGetLastError());

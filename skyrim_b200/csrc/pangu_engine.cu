@@ -340,21 +340,17 @@ struct PanguEngine : Engine {
     }
     {  // projection + LayerNorm + residual
       AImage A{ws.atth, ws.atth, nkb, 0};
-      Epi2F32Img<true, true> e{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
-      static const char* exp_env = getenv("SKY_EXP");  // timing experiments only (results invalid)
-      const int ex = exp_env ? atoi(exp_env) : 0;
-      if (ex == 1) e.img = nullptr;
-      if (ex == 2) {
-        Epi2F32Img<true, false> e3{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
-        rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e3, b.proj, R, ws.scratch, st)
-                      : gemm2<384, 8>(KT_PROJ, A, e3, b.proj, R, ws.scratch, st);
-      } else
+      EpiLnRes e{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
+      static const int ln_exp = getenv("SKY_LN_EXP") ? atoi(getenv("SKY_LN_EXP")) : 0;  // timing experiments only
+      e.exp = ln_exp;
       rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
                     : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
       if (rc) return rc;
     }
     if (!use_ref) {  // fused MLP: fc1 + GELU + fc2 + LayerNorm + residual, hidden stays on the SM
-      Epi2F32Img<true, true> e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      EpiLnRes e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      static const int ln_exp2 = getenv("SKY_LN_EXP") ? atoi(getenv("SKY_LN_EXP")) : 0;  // timing experiments only
+      e2.exp = ln_exp2;
       const KTag tag = (prof_split && C == 384) ? KT_FC2 : KT_MLP;
       prof_begin(tag, st);
       count_launch();
@@ -371,7 +367,7 @@ struct PanguEngine : Engine {
       Epi2F16<true, true> e{reinterpret_cast<__half*>(ws.hidh), 0, 4 * nkb, b.fc1_b};
       if ((rc = gemm2<192, 8>(KT_FC1, A, e, b.fc1, R, ws.scratch, st))) return rc;
       AImage A2{ws.hidh, ws.hidh, 4 * nkb, 0};
-      Epi2F32Img<true, true> e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      EpiLnRes e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
       rc = C == 192 ? gemm2<192, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st)
                     : gemm2<384, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st);
       if (rc) return rc;

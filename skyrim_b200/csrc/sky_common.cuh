@@ -143,6 +143,24 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
+// 256-bit global accesses (sm_100, PTX 8.8): one full 32-byte sector per lane.  Used by the
+// row-owner epilogues, where lane i owns token row i and the warp touches 32 different lines.
+__device__ __forceinline__ void ldg_f32x8(const float* p, float* v) {
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_f32x8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg_b32x8(void* p, uint4 lo, uint4 hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z),
+               "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 // Byte offset of element (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile whose rows
 // are 128 bytes (64 halves): Swizzle<3,4,3> — chunk index XOR (row mod 8).
 __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
