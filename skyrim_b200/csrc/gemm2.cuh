@@ -262,20 +262,24 @@ struct Epi2F16 {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
     const uint32_t r0 = (uint32_t)(x.row0 & 127);
     for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
-      float v[32];
-      acc.load32(c, v);
-      // bias + activation in the row domain: 32 independent dependency chains per thread
-      const float4* bp = reinterpret_cast<const float4*>(bias + x.n0 + c);
+      // this lane's 8 output columns are the same for all its rows: their bias is loaded once, ahead of the TMEM read
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8 + 4));
+      {
+        float v[32];
+        acc.load32(c, v);
+        if (kGelu) {
+          // activation in the row domain: 32 independent dependency chains per thread
+          const float4* bp = reinterpret_cast<const float4*>(bias + x.n0 + c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(bp + j);
-        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bp + j);
+            gelu_erf_x2(v[4 * j], v[4 * j + 1], b.x, b.y);
+            gelu_erf_x2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
+          }
+        }
+        patch_put_v(x.patch_s, x.lane, v);
       }
-      if (kGelu) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1], 0.f, 0.f);
-      }
-      patch_put_s(x.patch_s, x.lane, v);
       __syncwarp();
       const int col = x.n0 + c;  // first column of the chunk
       uint8_t* ibase = nullptr;
@@ -284,7 +288,15 @@ struct Epi2F16 {
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + rsub;
-        const uint4 pk = patch_get_h8(x.patch_s, rr, ch * 8);
+        float4 t0 = lds_f32x4(x.patch_s + (rr * G2_PATCHV_LD + ch * 8) * 4);
+        float4 t1 = lds_f32x4(x.patch_s + (rr * G2_PATCHV_LD + ch * 8 + 4) * 4);
+        if (!kGelu) {
+          t0.x += b0.x; t0.y += b0.y; t0.z += b0.z; t0.w += b0.w;
+          t1.x += b1.x; t1.y += b1.y; t1.z += b1.z; t1.w += b1.w;
+        }
+        uint4 pk;
+        pk.x = pack_half2(t0.x, t0.y); pk.y = pack_half2(t0.z, t0.w);
+        pk.z = pack_half2(t1.x, t1.y); pk.w = pack_half2(t1.z, t1.w);
         if (x.row0 + rr < x.M) {
           if (kImage)
             *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;

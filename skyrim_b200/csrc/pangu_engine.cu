@@ -20,6 +20,7 @@
 #include "gemm_tc.cuh"
 #include "mlp_fused.cuh"
 #include "mlp_fused2.cuh"
+#include "gemm_pair.cuh"
 
 namespace sky {
 
@@ -129,6 +130,7 @@ struct PanguEngine : Engine {
   bool use_ref = false;
   // fused MLP on CTA pairs (cta_group::2) per channel width; SKY_MLP=1cta|pair192|pair384 selects for A/B timing
   bool mlp_pair192 = true, mlp_pair384 = true;
+  bool qkv_pair = true;     // SKY_QKV=1cta selects k_gemm2 for the QKV projection (A/B timing)
   bool prof_split = false;  // SKY_PROF_SPLIT: report the C=384 MLP launches under the (otherwise unused) fc2 tag
   std::vector<void*> owned;
   GemmW embed_u, embed_s, down, up1, up2, rec;
@@ -159,6 +161,8 @@ struct PanguEngine : Engine {
     if (m && !strcmp(m, "pair192")) mlp_pair384 = false;
     if (m && !strcmp(m, "pair384")) mlp_pair192 = false;
     prof_split = getenv("SKY_PROF_SPLIT") != nullptr;
+    const char* qv = getenv("SKY_QKV");
+    qkv_pair = !(qv && !strcmp(qv, "1cta"));
   }
   ~PanguEngine() override {
     for (void* p : owned) cudaFree(p);
@@ -327,7 +331,16 @@ struct PanguEngine : Engine {
     {  // QKV projection on natural-order tokens
       AImage A{xh, xh, nkb, 0};
       Epi2F16<false, false> e{ws.qkv, 3 * C, 0, b.qkv_b};
-      if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
+      if (use_ref || !qkv_pair) {
+        if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
+      } else {  // A-stationary CTA-pair kernel: a third of the L2 traffic of the tile-streaming kernel
+        prof_begin(KT_QKV, st);
+        count_launch();
+        rc = C == 192 ? launch_gemm_pair<Epi2F16<false, false>, 192>(xh, e, b.qkv.img, R, 3 * C, num_sms, st)
+                      : launch_gemm_pair<Epi2F16<false, false>, 384>(xh, e, b.qkv.img, R, 3 * C, num_sms, st);
+        prof_end(KT_QKV, st);
+        if (rc) return rc;
+      }
     }
     {
       dim3 grid(g.heads, (unsigned)(B * g.nWin));
