@@ -20,8 +20,8 @@ namespace sky {
 constexpr int G2_BLOCK_M = 128;
 constexpr int G2_A_BYTES = G2_BLOCK_M * 128;
 constexpr int G2_PATCH_LD = 33;    // scalar accessors (odd stride: conflict-free column reads)
-constexpr int G2_PATCHV_LD = 36;   // 128-bit accessors (row stride 144 B: conflict-free per quarter warp both ways)
-constexpr int G2_PATCH_FLOATS = 32 * G2_PATCHV_LD;
+constexpr int G2_PATCH_FLOATS = 32 * G2_PATCH_LD;
+constexpr int G2_PATCHV_BYTES = 4096;   // 128-bit accessors: 32 rows x 128 B, 16-byte chunk index XOR (row & 7)
 
 // element (row, col) of an fp16 tile image with nkb k-blocks per row tile -> byte offset
 __device__ __forceinline__ size_t img_offset(long long row, int col, int nkb) {
@@ -73,6 +73,7 @@ struct EpiCtx {
   uint32_t patch_s;    // the same patch as a shared-space address
   uint32_t svec_s;     // shared-space address of bias | gamma | beta, vstride floats apart (LN epilogues)
   int vstride = 512;
+  int patch_stride = G2_PATCH_FLOATS * 4;   // bytes between the patches of consecutive warps
 };
 
 struct AccTmem2 {
@@ -231,12 +232,18 @@ __device__ __forceinline__ void patch_put_s(uint32_t patch_s, int lane, const fl
 #pragma unroll
   for (int j = 0; j < 32; ++j) sts_f32(a + 4 * j, v[j]);
 }
-// row-owner write of a 32x32 fp32 block with 128-bit stores (patch stride G2_PATCHV_LD)
+// 32x32 fp32 block in the swizzled vector layout (G2_PATCHV_BYTES): row r is 128 bytes, its 16-byte chunk k sits at
+// position k ^ (r & 7).  Row-owner writes (lane = row, all chunks) and re-tiled reads (8 lanes = the 8 chunks of one
+// row) are both conflict-free per quarter warp, with no padding: 16 patches fit in 64 KB.
+__device__ __forceinline__ uint32_t patchv_addr(uint32_t patch_s, int r, int k) {
+  return patch_s + (uint32_t)r * 128u + ((uint32_t)(k ^ (r & 7)) << 4);
+}
 __device__ __forceinline__ void patch_put_v(uint32_t patch_s, int lane, const float (&v)[32]) {
-  const uint32_t a = patch_s + lane * (G2_PATCHV_LD * 4);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4)
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 4 * j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+  for (int k = 0; k < 8; ++k)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(patchv_addr(patch_s, lane, k)), "f"(v[4 * k]), "f"(v[4 * k + 1]),
+                 "f"(v[4 * k + 2]), "f"(v[4 * k + 3])
+                 : "memory");
 }
 // 8 consecutive floats of patch row rr starting at column c8 -> 8 halves
 __device__ __forceinline__ uint4 patch_get_h8(uint32_t patch_s, int rr, int c8) {
@@ -288,8 +295,8 @@ struct Epi2F16 {
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + rsub;
-        float4 t0 = lds_f32x4(x.patch_s + (rr * G2_PATCHV_LD + ch * 8) * 4);
-        float4 t1 = lds_f32x4(x.patch_s + (rr * G2_PATCHV_LD + ch * 8 + 4) * 4);
+        float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+        float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
         if (!kGelu) {
           t0.x += b0.x; t0.y += b0.y; t0.z += b0.z; t0.w += b0.w;
           t1.x += b1.x; t1.y += b1.y; t1.z += b1.z; t1.w += b1.w;
@@ -340,7 +347,9 @@ struct Epi2F32Img {
   // fp16 image chunks (8 columns = 16 bytes) are assembled from lane pairs by shuffle, not through
   // shared memory.  Every warp reduces the statistics of its own column groups only; the warps that
   // share a lane quarter exchange partial sums through their patches.
-  template <int BN, class Acc>
+  // kPrefetch: load the residual of the next column group while this one is processed (32 more registers; kernels
+  // with 16 epilogue warps hide the latency with occupancy instead)
+  template <int BN, bool kPrefetch = true, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& e) const {
     constexpr int NG = BN / 32;
     const int rsub4 = e.lane >> 3, c4 = e.lane & 7;
@@ -351,8 +360,8 @@ struct Epi2F32Img {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rr = it * 4 + rsub4;
-      xin[it] = (ld_on && rr < rows_left && e.part < NG) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      xin[it] = (kPrefetch && ld_on && rr < rows_left && e.part < NG) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float rs[8], ns[8];   // rstd and -mean*rstd of row it*4 + rsub4
 #pragma unroll
@@ -378,7 +387,7 @@ struct Epi2F32Img {
         for (int p = 0; p < e.nparts; ++p) {
           if (p == e.part) continue;
           float ps, pss;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(slot + (p - e.part) * 4 * G2_PATCH_FLOATS * 4));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(slot + (p - e.part) * 4 * e.patch_stride));
           s += ps; ss += pss;
         }
         asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(32 * e.nparts) : "memory");   // the patches are reused below
@@ -396,6 +405,13 @@ struct Epi2F32Img {
     const int odd = e.lane & 1;
     for (int g = e.part; g < NG; g += e.nparts) {
       const int c = g * 32;
+      if (!kPrefetch && kResidual) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub4;
+          xin[it] = (ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       {
         float v[32];
         acc.load32(c, v);
@@ -411,8 +427,8 @@ struct Epi2F32Img {
         bs = __ldg(reinterpret_cast<const float4*>(bias + e.n0 + c + c4 * 4));
       }
       const bool more = g + e.nparts < NG;
-      float4 xnext[8];
-      if (kResidual) {
+      float4 xnext[kPrefetch ? 8 : 1];
+      if constexpr (kResidual && kPrefetch) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + rsub4;
@@ -430,7 +446,7 @@ struct Epi2F32Img {
         for (int u = 0; u < 2; ++u) {
           const int it = it2 + u;
           const int rr = it * 4 + rsub4;
-          const float4 t = lds_f32x4(e.patch_s + (rr * G2_PATCHV_LD + c4 * 4) * 4);
+          const float4 t = lds_f32x4(patchv_addr(e.patch_s, rr, c4));
           float4 y;
           y.x = fmaf(fmaf(t.x + bs.x, rs[it], ns[it]), ga.x, be.x); y.y = fmaf(fmaf(t.y + bs.y, rs[it], ns[it]), ga.y, be.y);
           y.z = fmaf(fmaf(t.z + bs.z, rs[it], ns[it]), ga.z, be.z); y.w = fmaf(fmaf(t.w + bs.w, rs[it], ns[it]), ga.w, be.w);
@@ -450,7 +466,7 @@ struct Epi2F32Img {
         }
       }
       __syncwarp();
-      if (kResidual) {
+      if constexpr (kResidual && kPrefetch) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) xin[it] = xnext[it];
       }

@@ -244,7 +244,7 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
     const int q = warp & 3, part = warp >> 2;
     EpiCtx ctx;
     ctx.M = M; ctx.lane = lane; ctx.part = part; ctx.nparts = 2; ctx.n0 = 0;
-    ctx.patch = reinterpret_cast<float*>(hid_s) + warp * G2_PATCH_FLOATS;
+    ctx.patch = reinterpret_cast<float*>(hid_s) + warp * G2_PATCH_FLOATS;   // 8 x 4.2 KB inside the 64 KB hidden region
     ctx.patch_s = smem_u32(ctx.patch);
     ctx.svec_s = smem_u32(lnv);
     ctx.vstride = C;
