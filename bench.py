@@ -279,7 +279,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dominant, "achieved": achieved,
                          "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tensor_sustained"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["tensor_sustained"]) if achieved else None, "traffic": _traffic(dominant),
                          "peak_source": peaks["source"] + " bf16 cuBLAS, sustained (kernel timed inside a long step)",
                          "launches_per_step": n_l, "avg_launch_ms": avg_ms,
                          "step_tflops": M * fl["total"] / (ms_step * 1e-3) / 1e12},
@@ -289,6 +289,17 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _traffic(family):
+    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json, provenance inside); None when no capture covers the family."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(family, {}).get("bytes_per_launch")
+    except (OSError, ValueError):
+        return None
 
 
 def main():

@@ -37,7 +37,8 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // partition, the cyclic shift and the latitude padding are index arithmetic here and nowhere
 // else; a padding token has x = 0, so its q/k/v are the QKV bias.  Output: fp16 tile image of
 // (tokens, C) (A operand of the projection GEMM), again in natural order.
-__global__ void __launch_bounds__(ATT_THREADS)
+// 5 CTAs / SM: the register file allocates 512 registers per warp-granule, so 130 registers cost a whole CTA of occupancy
+__global__ void __launch_bounds__(ATT_THREADS, 5)
 k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img, int att_nkb,
                    const __half* __restrict__ bias_tab, const float* __restrict__ qkv_bias, Geo g, int roll,
                    float scale, float mask_value) {
