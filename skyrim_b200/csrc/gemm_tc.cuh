@@ -80,23 +80,23 @@ k_gemm_tc(const Prod prod, const Epi epi, const uint8_t* __restrict__ Wimg, long
 
   if (warp >= 4 && warp < 8) {
     // ============================ A producers ============================
-    const int p = threadIdx.x - 128;
-    const int chunk = p & 7, r0 = p >> 3;  // rows r0 + 16*i
+    // thread = tile row, the 8 chunks of a k-block in sequence: for one chunk the 32 lanes of a warp are 32
+    // consecutive tokens, i.e. one contiguous 512-byte run of the source field per load instruction, and the
+    // 16-byte shared-memory stores of a quarter warp fall into 8 different swizzled chunk slots
+    const int row = threadIdx.x - 128;
     int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long m0 = (long long)(tile / num_n_tiles) * TC_BLOCK_M;
-      RowInfo ri[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ri[i] = prod.prep(m0 + r0 + 16 * i);
+      const RowInfo ri = prod.prep(m0 + row);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* a_s = smem + s * Cfg::STAGE_BYTES;
         uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = prod.load8(ri[i], kb * TC_BLOCK_K + chunk * 8);
+        for (int i = 0; i < 8; ++i) v[i] = prod.load8(ri, kb * TC_BLOCK_K + i * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(a_s + sw128_offset(r0 + 16 * i, chunk)) = v[i];
+          *reinterpret_cast<uint4*>(a_s + sw128_offset(row, i)) = v[i];
         fence_proxy_async_smem();
         mbar_arrive(&full[s]);
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }

@@ -204,27 +204,32 @@ struct EpiStoreF32 {
       float v[32];
       acc.load32(c, v);
       if (row < M) {
-        float4* o = reinterpret_cast<float4*>(out + dst * ldo + n0 + c);
+        if (bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (bias) {
-            float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c) + j);
-            t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c) + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
           }
-          o[j] = t;
-          v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
         }
+        // the lane owns its row: 256-bit stores, one full 32-byte sector per lane and instruction
+        float* o = out + dst * ldo + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg_f32x8(o + 8 * j, v + 8 * j);
         if (img) {
           const int col = n0 + c;
-          uint8_t* base = img + ((size_t)(dst >> 7) * nkb + (col >> 6)) * 16384;
-          const uint32_t r = (uint32_t)(dst & 127);
+          uint8_t* base = img + ((size_t)(dst >> 7) * nkb + (col >> 6)) * 16384 + (size_t)(dst & 127) * 128;
+          const uint32_t r7 = (uint32_t)dst & 7u, cb = ((uint32_t)col & 63u) >> 3;   // cb = 0 or 4
+          // SWIZZLE_128B permutes 16-byte chunks by XOR with (row & 7): an aligned chunk pair stays an aligned pair
+          // (halves swapped when bit 0 of the row is set), so two chunks go out as one 32-byte store
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            pk.x = pack_half2(v[8 * j], v[8 * j + 1]); pk.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-            pk.z = pack_half2(v[8 * j + 4], v[8 * j + 5]); pk.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(base + sw128_offset(r, ((col & 63) >> 3) + j)) = pk;
+          for (int m = 0; m < 2; ++m) {
+            uint4 c0, c1;
+            c0.x = pack_half2(v[16 * m], v[16 * m + 1]); c0.y = pack_half2(v[16 * m + 2], v[16 * m + 3]);
+            c0.z = pack_half2(v[16 * m + 4], v[16 * m + 5]); c0.w = pack_half2(v[16 * m + 6], v[16 * m + 7]);
+            c1.x = pack_half2(v[16 * m + 8], v[16 * m + 9]); c1.y = pack_half2(v[16 * m + 10], v[16 * m + 11]);
+            c1.z = pack_half2(v[16 * m + 12], v[16 * m + 13]); c1.w = pack_half2(v[16 * m + 14], v[16 * m + 15]);
+            const uint32_t pr = ((cb >> 1) + m) ^ (r7 >> 1);
+            if (r7 & 1u) stg_b32x8(base + pr * 32, c1, c0); else stg_b32x8(base + pr * 32, c0, c1);
           }
         }
       }
