@@ -264,6 +264,7 @@ struct Epi2F16 {
   static constexpr bool kNeedsBias = false;
   __half* out; int ldo; int nkb; const float* bias;
   const float* gamma = nullptr; const float* beta = nullptr;  // unused (uniform epilogue interface)
+  int exp = 0;  // timing experiments only (results invalid): 2 = no global stores
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& x) const {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
@@ -304,11 +305,13 @@ struct Epi2F16 {
         uint4 pk;
         pk.x = pack_half2(t0.x, t0.y); pk.y = pack_half2(t0.z, t0.w);
         pk.z = pack_half2(t1.x, t1.y); pk.w = pack_half2(t1.z, t1.w);
-        if (x.row0 + rr < x.M) {
+        if (x.row0 + rr < x.M && !(exp & 2)) {
           if (kImage)
             *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
           else
             *reinterpret_cast<uint4*>(out + (x.row0 + rr) * ldo + col + ch * 8) = pk;
+        } else if (exp & 2) {
+          asm volatile("" ::"r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w));   // keep the value alive
         }
       }
       __syncwarp();

@@ -331,6 +331,8 @@ struct PanguEngine : Engine {
     {  // QKV projection on natural-order tokens
       AImage A{xh, xh, nkb, 0};
       Epi2F16<false, false> e{ws.qkv, 3 * C, 0, b.qkv_b};
+      static const int qkv_exp = getenv("SKY_QKV_EXP") ? atoi(getenv("SKY_QKV_EXP")) : 0;  // timing experiments only
+      e.exp = qkv_exp;
       if (use_ref || !qkv_pair) {
         if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
       } else {  // A-stationary CTA-pair kernel: a third of the L2 traffic of the tile-streaming kernel
