@@ -160,3 +160,34 @@ def test_engine_errors_are_loud(small):
     with pytest.raises(_ffi.SkyError):
         eng.load_weights(bad)
     eng.close()
+
+
+def _engine_env(cfg, w, **env):
+    from skyrim_b200.engine import StepEngine
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        eng = StepEngine(cfg, 0)   # the kernel selection switches are read when the engine is created
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    eng.load_weights(w)
+    return eng
+
+
+def test_cta_pair_kernels_agree_with_single_cta_kernels(small):
+    """The cta_group::2 kernels (fused MLP, QKV projection) against the single-CTA kernels they replaced: same
+    fp16 operands and fp32 accumulation, different tiling -> agreement far inside the oracle tolerance, and
+    both inside the tolerance against the oracle.  41x96 gives 17 row tiles per member: the odd tile of the
+    last pair (one CTA idle) is covered."""
+    from oracle.pangu_ref import rel_err_per_channel
+    cfg, w, x0, ref = small
+    x = torch.from_numpy(x0)[None].cuda()
+    pair = _engine_env(cfg, w)
+    single = _engine_env(cfg, w, SKY_MLP="1cta", SKY_QKV="1cta")
+    yp = pair.step(x)[0].cpu().numpy()
+    ys = single.step(x)[0].cpu().numpy()
+    yr = ref.step(x0).numpy()
+    assert rel_err_per_channel(yp, ys).max() < 2e-4, rel_err_per_channel(yp, ys).max()
+    assert rel_err_per_channel(yp, yr).max() < TOL and rel_err_per_channel(ys, yr).max() < TOL
+    pair.close(); single.close()
