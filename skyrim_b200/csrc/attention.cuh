@@ -33,7 +33,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid (heads, total windows).  qkv: (tokens, 3C) fp16 in NATURAL token order — the window
+// grid (heads, total windows).  qkv: (3, heads, tokens, 32) fp16, tokens in NATURAL order — the window
 // partition, the cyclic shift and the latitude padding are index arithmetic here and nowhere
 // else; a padding token has x = 0, so its q/k/v are the QKV bias.  Output: fp16 tile image of
 // (tokens, C) (A operand of the projection GEMM), again in natural order.
@@ -41,7 +41,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 __global__ void __launch_bounds__(ATT_THREADS, 5)
 k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img, int att_nkb,
                    const __half* __restrict__ bias_tab, const float* __restrict__ qkv_bias, Geo g, int roll,
-                   float scale, float mask_value) {
+                   float scale, float mask_value, long long rows /* tokens of all stacked members */) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* Qs = reinterpret_cast<__half*>(att_smem);
   __half* Ks = Qs + WIN_TOK * ATT_LDS;
@@ -75,7 +75,7 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
     __half* dst = Qs + part * WIN_TOK * ATT_LDS + row * ATT_LDS + ch * 8;
     const long long t = tok[row];
     if (t >= 0) {
-      cp_async16(dst, qkv + t * 3 * C + part * C + head * 32 + ch * 8);
+      cp_async16(dst, qkv + (((size_t)part * g.heads + head) * rows + t) * 32 + ch * 8);
     } else {
       const float* bq = qkv_bias + part * C + head * 32 + ch * 8;
       uint4 pk;

@@ -265,6 +265,10 @@ struct Epi2F16 {
   __half* out; int ldo; int nkb; const float* bias;
   const float* gamma = nullptr; const float* beta = nullptr;  // unused (uniform epilogue interface)
   int exp = 0;  // timing experiments only (results invalid): 2 = no global stores
+  // head_major (row-major mode only): column block j of 32 goes to out[j][row][0..32), i.e. (part, head, token, 32) for
+  // the QKV projection.  A warp store then covers 8 consecutive tokens x 64 B = 512 contiguous bytes instead of 8
+  // half lines 2*ldo bytes apart, and the attention kernel reads 64-byte rows that are contiguous along longitude.
+  int head_major = 0;
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& x) const {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
@@ -308,6 +312,8 @@ struct Epi2F16 {
         if (x.row0 + rr < x.M && !(exp & 2)) {
           if (kImage)
             *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
+          else if (head_major)
+            *reinterpret_cast<uint4*>(out + ((size_t)((col + ch * 8) >> 5) * x.M + (x.row0 + rr)) * 32 + ((col + ch * 8) & 31)) = pk;
           else
             *reinterpret_cast<uint4*>(out + (x.row0 + rr) * ldo + col + ch * 8) = pk;
         } else if (exp & 2) {

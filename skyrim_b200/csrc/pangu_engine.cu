@@ -333,6 +333,7 @@ struct PanguEngine : Engine {
       Epi2F16<false, false> e{ws.qkv, 3 * C, 0, b.qkv_b};
       static const int qkv_exp = getenv("SKY_QKV_EXP") ? atoi(getenv("SKY_QKV_EXP")) : 0;  // timing experiments only
       e.exp = qkv_exp;
+      e.head_major = 1;   // (3, heads, tokens, 32): what k_window_attention reads
       if (use_ref || !qkv_pair) {
         if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
       } else {  // A-stationary CTA-pair kernel: a third of the L2 traffic of the tile-streaming kernel
@@ -348,7 +349,7 @@ struct PanguEngine : Engine {
       dim3 grid(g.heads, (unsigned)(B * g.nWin));
       prof_begin(KT_ATTN, st);
       k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.atth, nkb, b.bias_tab, b.qkv_b, g, roll,
-                                                                  rsqrtf(32.f), cfg.mask_value);
+                                                                  rsqrtf(32.f), cfg.mask_value, R);
       prof_end(KT_ATTN, st);
       count_launch();
       SKY_CUDA_OK(cudaGetLastError());
