@@ -76,15 +76,18 @@ __global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__
   if (row >= rows) return;
   int w2 = (int)(row % W2); long long q = row / W2;
   int h2 = (int)(q % H2); q /= H2;  // q = member*Z + z
+  // lane owns 4 consecutive features per 128-feature slab: 128-bit loads, 64-bit image stores
+  static_assert(NPL % 4 == 0, "features per lane");
   float v[NPL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    int e = lane + 32 * i;  // feature index in (hs, ws, c)
-    int sub = e / C, c = e % C;
-    int h = 2 * h2 + (sub >> 1), w = 2 * w2 + (sub & 1);
-    v[i] = h < H ? x[((q * H + h) * W + w) * C + c] : 0.f;
-    s += v[i];
+  for (int i = 0; i < NPL / 4; ++i) {
+    const int e = 4 * lane + 128 * i;  // feature index in (hs, ws, c); C % 4 == 0, so the four share (hs, ws)
+    const int sub = e / C, c = e % C;
+    const int h = 2 * h2 + (sub >> 1), w = 2 * w2 + (sub & 1);
+    const float4 t = h < H ? __ldg(reinterpret_cast<const float4*>(x + ((q * H + h) * W + w) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    s += (t.x + t.y) + (t.z + t.w);
   }
   float mean = warp_sum(s) / (NPL * 32);
   float ss = 0.f;
@@ -92,10 +95,13 @@ __global__ void __launch_bounds__(256) k_down_merge_ln(const float* __restrict__
   for (int i = 0; i < NPL; ++i) { float d = v[i] - mean; ss += d * d; }
   float rstd = rsqrtf(warp_sum(ss) / (NPL * 32) + eps);
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    int e = lane + 32 * i;
-    *reinterpret_cast<__half*>(img + img_offset(row, e, NPL / 2)) =
-        __float2half_rn((v[i] - mean) * rstd * gamma[e] + beta[e]);
+  for (int i = 0; i < NPL / 4; ++i) {
+    const int e = 4 * lane + 128 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e)), b = __ldg(reinterpret_cast<const float4*>(beta + e));
+    uint2 pk;
+    pk.x = pack_half2((v[4 * i] - mean) * rstd * g.x + b.x, (v[4 * i + 1] - mean) * rstd * g.y + b.y);
+    pk.y = pack_half2((v[4 * i + 2] - mean) * rstd * g.z + b.z, (v[4 * i + 3] - mean) * rstd * g.w + b.w);
+    *reinterpret_cast<uint2*>(img + img_offset(row, e, NPL / 2)) = pk;
   }
 }
 
