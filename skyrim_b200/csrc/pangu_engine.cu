@@ -412,20 +412,19 @@ struct PanguEngine : Engine {
     {
       long long M = (long long)B * nzt * HW;
       ProdEmbedUpper p{x_in, mean, stdv, cfg.nlat, cfg.nlon, cfg.n_levels, 5, nch, g1.H, g1.W, nzt, M};
-      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW, ws.x1h, C / 64};
+      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW, ws.skiph, C / 64};
       if ((rc = gemm_prod<192>(KT_EMBED, p, e, embed_u, M, ws.scratch, st))) return rc;
       long long Ms = (long long)B * HW;
       ProdEmbedSurf ps{x_in, masks, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 4, 3, g1.H, g1.W, Ms};
-      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW, ws.x1h, C / 64};
+      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW, ws.skiph, C / 64};
       if ((rc = gemm_prod<192>(KT_EMBED, ps, es, embed_s, Ms, ws.scratch, st))) return rc;
     }
     if (stop == 0) return 0;
     for (size_t i = 0; i < blocks[0].size(); ++i)
-      if ((rc = run_block(ws.x1, ws.x1h, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
+      if ((rc = run_block(ws.x1, ws.skiph, g1, blocks[0][i], (int)(i & 1), B, ws, st))) return rc;
     if (stop == 1) return 0;
-    prof_begin(KT_COPY, st);
-    SKY_CUDA_OK(cudaMemcpyAsync(ws.skiph, ws.x1h, ws.x1h_bytes, cudaMemcpyDeviceToDevice, st));
-    prof_end(KT_COPY, st);
+    // the first layer works in place on the skip image: its final operand image IS the skip connection that patch
+    // recovery concatenates, the up-sample path writes the other image (x1h) — no copy
     // ---- down-sample ----
     {
       prof_begin(KT_DOWN, st);
