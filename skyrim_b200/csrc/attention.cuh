@@ -59,9 +59,21 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
   const int C = g.C;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
+  // natural token of window row j (same mapping as win_row_to_token, with the window coordinates — 64-bit divisions by
+  // run-time values — taken out of the per-token loop: they were ~15 % of the kernel's instructions)
+  const int wwi = win % g.nWw;
+  const long long mbase = (wing / g.nWin) * g.T;
   for (int j = tid; j < WIN_TOK; j += ATT_THREADS) {
-    tok[j] = win_row_to_token(g, roll, wing * WIN_TOK + j);
     int wj = j % WW, hj = (j / WW) % WH, zj = j / (WW * WH);
+    {
+      int z = wzi * WZ + zj, h = whi * WH + hj, w = wwi * WW + wj;
+      if (roll) {
+        z += SZ; if (z >= g.Z) z -= g.Z;
+        h += SH; if (h >= g.Hp) h -= g.Hp;
+        w += SW; if (w >= g.W) w -= g.W;
+      }
+      tok[j] = h >= g.H ? -1 : mbase + ((long long)z * g.H + h) * g.W + w;
+    }
     int part = (WZ * zj) * ((2 * WW - 1) * WH * WH) + (WH * hj) * (2 * WW - 1) - wj;
     colpart[j] = part + 64;  // +64 keeps it non-negative (the row part carries -64)
     colflag[j] = (zj >= WZ - SZ ? 1 : 0) | (hj >= WH - SH ? 2 : 0);
