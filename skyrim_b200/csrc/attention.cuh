@@ -33,7 +33,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid (heads, total windows).  qkv: (3, heads, tokens, 32) fp16, tokens in NATURAL order — the window
+// grid (heads, windows, members).  qkv: (3, heads, tokens, 32) fp16, tokens in NATURAL order — the window
 // partition, the cyclic shift and the latitude padding are index arithmetic here and nowhere
 // else; a padding token has x = 0, so its q/k/v are the QKV bias.  Output: fp16 tile image of
 // (tokens, C) (A operand of the projection GEMM), again in natural order.
@@ -51,18 +51,18 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
   int* colflag = colpart + WIN_TOK;                       // per key token: seam side flags (z: 1, lat: 2)
   long long* tok = reinterpret_cast<long long*>(colflag + WIN_TOK);
 
+  // grid (heads, windows of one member, members): no 64-bit division by run-time values anywhere in the kernel
   const int head = blockIdx.x;
-  const long long wing = blockIdx.y;           // global window index (members stacked)
-  const int win = (int)(wing % g.nWin);
-  const int type = win / g.nWw;                // (z-window, lat-window)
-  const int whi = type % g.nWh, wzi = type / g.nWh;
+  const int win = blockIdx.y;
+  const unsigned type = (unsigned)win / (unsigned)g.nWw;   // (z-window, lat-window)
+  const int wzi = (int)(type / (unsigned)g.nWh), whi = (int)type - wzi * g.nWh;
   const int C = g.C;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 
   // natural token of window row j (same mapping as win_row_to_token, with the window coordinates — 64-bit divisions by
   // run-time values — taken out of the per-token loop: they were ~15 % of the kernel's instructions)
-  const int wwi = win % g.nWw;
-  const long long mbase = (wing / g.nWin) * g.T;
+  const int wwi = win - (int)type * g.nWw;
+  const long long mbase = (long long)blockIdx.z * g.T;
   for (int j = tid; j < WIN_TOK; j += ATT_THREADS) {
     int wj = j % WW, hj = (j / WW) % WH, zj = j / (WW * WH);
     {
@@ -82,18 +82,29 @@ k_window_attention(const __half* __restrict__ qkv, uint8_t* __restrict__ att_img
   for (int i = tid; i < ATT_TABLE / 8; i += ATT_THREADS) cp_async16(Bs + 8 * i, bsrc + 8 * i);
   __syncthreads();
   // ---- stage Q, K, V (64 B per token each) ----
-  for (int i = tid; i < WIN_TOK * 12; i += ATT_THREADS) {
-    int row = i / 12, rem = i % 12, part = rem / 4, ch = rem % 4;
-    __half* dst = Qs + part * WIN_TOK * ATT_LDS + row * ATT_LDS + ch * 8;
-    const long long t = tok[row];
-    if (t >= 0) {
-      cp_async16(dst, qkv + (((size_t)part * g.heads + head) * rows + t) * 32 + ch * 8);
-    } else {
-      const float* bq = qkv_bias + part * C + head * 32 + ch * 8;
-      uint4 pk;
-      pk.x = pack_half2(bq[0], bq[1]); pk.y = pack_half2(bq[2], bq[3]);
-      pk.z = pack_half2(bq[4], bq[5]); pk.w = pack_half2(bq[6], bq[7]);
-      *reinterpret_cast<uint4*>(dst) = pk;
+  // 4 threads per token row, 24 rows per pass: with the (part, head, token, 32) layout the 12 tokens of a window row are
+  // 768 contiguous bytes, and every address below is one 64-bit multiply-add on per-thread constants
+  {
+    const int ch = tid & 3, rsub = tid >> 2;
+    const size_t pstride = (size_t)g.heads * rows * 32;
+    const __half* src0 = qkv + (size_t)head * rows * 32 + ch * 8;
+#pragma unroll
+    for (int r0 = 0; r0 < WIN_TOK; r0 += ATT_THREADS / 4) {
+      const int row = r0 + rsub;
+      const long long t = tok[row];
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        __half* dst = Qs + (part * WIN_TOK + row) * ATT_LDS + ch * 8;
+        if (t >= 0) {
+          cp_async16(dst, src0 + part * pstride + t * 32);
+        } else {
+          const float* bq = qkv_bias + part * C + head * 32 + ch * 8;
+          uint4 pk;
+          pk.x = pack_half2(bq[0], bq[1]); pk.y = pack_half2(bq[2], bq[3]);
+          pk.z = pack_half2(bq[4], bq[5]); pk.w = pack_half2(bq[6], bq[7]);
+          *reinterpret_cast<uint4*>(dst) = pk;
+        }
+      }
     }
   }
   asm volatile("cp.async.commit_group;");

@@ -352,7 +352,7 @@ struct PanguEngine : Engine {
       }
     }
     {
-      dim3 grid(g.heads, (unsigned)(B * g.nWin));
+      dim3 grid(g.heads, (unsigned)g.nWin, (unsigned)B);
       prof_begin(KT_ATTN, st);
       k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.atth, nkb, b.bias_tab, b.qkv_b, g, roll,
                                                                   rsqrtf(32.f), cfg.mask_value, R);
