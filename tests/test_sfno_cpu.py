@@ -88,3 +88,18 @@ def test_three_term_fp16_split_is_fp32_grade():
     one = np.abs(f(ah, bh) - exact).max() / np.abs(exact).max()
     three = np.abs(f(ah, bh) + f(al, bh) + f(ah, bl) - exact).max() / np.abs(exact).max()
     assert one > 1e-4 and three < 3e-6, (one, three)
+
+
+def test_oracle_matches_golden():
+    """The fp32 oracle against the committed fp64 fixture (tools/make_golden.py): pins the restatement across
+    refactors; the reference itself ships no golden vector for this path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sfno_49x96_seed0.npz"))
+    cfg = sfno_small(49, 96, embed=64, layers=3)
+    w = make_sfno_weights(cfg, 0)
+    x0 = synthetic_state(FCNV2_CHANNELS, cfg.nlat, cfg.nlon, 0)
+    np.testing.assert_array_equal(x0[:, ::8, ::16], g["x0_sample"])
+    y = SFNORef(cfg, w, torch.float32).step(x0).numpy()
+    scale = np.abs(g["y_sample"]).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(y[:, ::6, ::12] - g["y_sample"]) / scale) < 1e-4
+    np.testing.assert_allclose(np.sqrt((y.astype(np.float64) ** 2).sum(axis=(1, 2))), g["y_norm"], rtol=1e-5)

@@ -21,3 +21,17 @@ np.savez_compressed(os.path.join(out, "pangu_41x96_seed0.npz"),
                     x0_sample=x0[:, ::8, ::16].astype(np.float32), y_sample=y[:, ::5, ::12],
                     y_norm=np.sqrt((y ** 2).sum(axis=(1, 2))), y_mean=y.mean(axis=(1, 2)))
 print("wrote", os.path.join(out, "pangu_41x96_seed0.npz"))
+
+# ---- FourCastNet-v2 SFNO (small configuration of tests/test_sfno_*.py) ----
+from skyrim_b200.config import sfno_small, FCNV2_CHANNELS
+from skyrim_b200.weights import make_sfno_weights
+from oracle.sfno_ref import SFNORef
+
+scfg = sfno_small(49, 96, embed=64, layers=3)
+sw = make_sfno_weights(scfg, 0)
+sx0 = synthetic_state(FCNV2_CHANNELS, scfg.nlat, scfg.nlon, 0)
+sy = SFNORef(scfg, sw, torch.float64).step(sx0).numpy()
+np.savez_compressed(os.path.join(out, "sfno_49x96_seed0.npz"),
+                    x0_sample=sx0[:, ::8, ::16].astype(np.float32), y_sample=sy[:, ::6, ::12],
+                    y_norm=np.sqrt((sy ** 2).sum(axis=(1, 2))), y_mean=sy.mean(axis=(1, 2)))
+print("wrote", os.path.join(out, "sfno_49x96_seed0.npz"))
