@@ -37,3 +37,26 @@ def test_sfno_step_parity(nlat, nlon, embed, layers):
     ref2 = SFNORef(cfg, w).step(ref).numpy()
     assert rel_err_per_channel(y2[0].cpu().numpy(), ref2).max() < 2 * TOL
     eng.close()
+
+
+def test_sfno_step_against_golden_fixture():
+    """CUDA engine against the committed fp64 fixture (tests/golden/sfno_49x96_seed0.npz, tools/make_golden.py):
+    sampled outputs and per-channel norms, no oracle evaluation in the loop."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    from skyrim_b200.config import FCNV2_CHANNELS, sfno_small
+    from skyrim_b200.engine import StepEngine
+    from skyrim_b200.weights import make_sfno_weights, sfno_tables, synthetic_state
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sfno_49x96_seed0.npz"))
+    cfg = sfno_small(49, 96, embed=64, layers=3)
+    w = make_sfno_weights(cfg, 0)
+    x0 = synthetic_state(FCNV2_CHANNELS, cfg.nlat, cfg.nlon, 0)
+    eng = StepEngine(cfg, 0)
+    allw = dict(w); allw.update(sfno_tables(cfg))
+    eng.load_weights(allw)
+    y = eng.step(torch.from_numpy(x0)[None].cuda())[0].cpu().numpy()
+    eng.close()
+    scale = np.abs(g["y_sample"]).max(axis=(1, 2), keepdims=True)
+    assert np.max(np.abs(y[:, ::6, ::12] - g["y_sample"]) / scale) < TOL
+    np.testing.assert_allclose(np.sqrt((y.astype(np.float64) ** 2).sum(axis=(1, 2))), g["y_norm"], rtol=TOL)
