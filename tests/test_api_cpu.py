@@ -125,3 +125,15 @@ def test_skyrim_facade_validates_names():
     assert Skyrim.list_available_models() == ["pangu", "fourcastnet_v2"]
     with pytest.raises(ValueError):
         Skyrim("not_a_model")
+
+
+def test_bench_traffic_lookup_reads_the_committed_ncu_numbers():
+    """bench.py's roofline.traffic comes from profiles/r1_traffic.json (one `ncu --set full` capture per round)."""
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    t = mod._traffic("mlp")
+    assert isinstance(t, int) and 3e8 < t < 2e9   # bytes per launch of the fused MLP (algorithmic: 0.75e9)
+    assert mod._traffic("no-such-family") is None
