@@ -22,21 +22,19 @@ import torch
 import torch.nn.functional as F
 
 from skyrim_b200.config import SFNOConfig
-from skyrim_b200.sht import RealSHT
+from oracle import sht_ref
 
 
 class SFNORef:
     def __init__(self, cfg: SFNOConfig, weights, dtype=torch.float32, emulate: str | None = None):
         self.cfg, self.dtype, self.emulate = cfg, dtype, emulate
         self.w = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in weights.items()}
-        np_dt = np.float64
-        big = RealSHT(cfg.nlat, cfg.nlon, cfg.lmax, cfg.mmax, "equiangular")
-        itl = RealSHT(cfg.h, cfg.w, cfg.lmax, cfg.mmax, "legendre-gauss")
         cd = torch.complex128 if dtype == torch.float64 else torch.complex64
+        # Legendre / quadrature tables from the oracle's OWN builder (scipy), not the product's skyrim_b200/sht.py
         self.tabs = {}
-        for tag, s in (("big", big), ("int", itl)):
-            self.tabs[tag] = dict(fwd=torch.from_numpy(s.fwd.astype(np_dt)).to(dtype), inv=torch.from_numpy(s.inv.astype(np_dt)).to(dtype),
-                                  nlon=s.nlon, nlat=s.nlat)
+        for tag, (nlat, nlon, grid) in (("big", (cfg.nlat, cfg.nlon, "equiangular")), ("int", (cfg.h, cfg.w, "legendre-gauss"))):
+            fwd, inv, _, _ = sht_ref.tables(nlat, cfg.lmax, cfg.mmax, grid)
+            self.tabs[tag] = dict(fwd=torch.from_numpy(fwd).to(dtype), inv=torch.from_numpy(inv).to(dtype), nlon=nlon, nlat=nlat)
         self.cd = cd
 
     def _q(self, t):

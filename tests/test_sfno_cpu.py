@@ -103,3 +103,34 @@ def test_oracle_matches_golden():
     scale = np.abs(g["y_sample"]).max(axis=(1, 2), keepdims=True)
     assert np.max(np.abs(y[:, ::6, ::12] - g["y_sample"]) / scale) < 1e-4
     np.testing.assert_allclose(np.sqrt((y.astype(np.float64) ** 2).sum(axis=(1, 2))), g["y_norm"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("nlat,grid", [(49, "equiangular"), (97, "equiangular"), (32, "legendre-gauss"), (80, "legendre-gauss")])
+def test_product_tables_agree_with_independent_oracle_tables(nlat, grid):
+    """skyrim_b200/sht.py (recurrence + cosine-sum Clenshaw-Curtis / numpy leggauss: what the engine's weight arena
+    carries) against oracle/sht_ref.py (scipy.special.sph_legendre_p, Waldvogel FFT weights, roots_legendre):
+    two algorithms, one convention — orthonormal Pbar with Condon-Shortley phase, north pole first."""
+    from oracle import sht_ref
+    from skyrim_b200.sht import sht_tables, grid_nodes
+    lmax, mmax = 33, 34
+    f1, i1, cost1, w1 = sht_ref.tables(nlat, lmax, mmax, grid)
+    f2, i2 = sht_tables(nlat, lmax, mmax, grid)
+    cost2, w2 = grid_nodes(nlat, grid)
+    assert np.abs(cost1 - cost2).max() < 1e-14 and np.abs(w1 - w2).max() < 1e-14
+    assert np.abs(f1 - f2).max() < 1e-12 and np.abs(i1 - i2).max() < 1e-12
+    # Condon-Shortley: Pbar_1^1(cos theta) = -sqrt(3/(8 pi)) sin(theta)
+    th = np.arccos(cost1)
+    assert np.abs(i1[1, :, 1] + np.sqrt(3.0 / (8.0 * np.pi)) * np.sin(th)).max() < 1e-14
+
+
+def test_full_size_fixtures_match_the_seeded_inputs():
+    """tests/golden/*_721x1440_seed0.npz (one real oracle step each, tools/make_golden_full.py): the committed IC
+    sample must equal what skyrim_b200.weights regenerates, or the GPU-side comparison would be meaningless."""
+    from skyrim_b200.config import PANGU_CHANNELS
+    from skyrim_b200.verify import load_fixture
+    for model, names in (("pangu", PANGU_CHANNELS), ("sfno", FCNV2_CHANNELS)):
+        fx = load_fixture(model)
+        x0 = synthetic_state(names, 721, 1440, 0)
+        np.testing.assert_array_equal(x0[:, ::64, ::64], fx["x0_sample"])
+        assert fx["y_sample"].shape == (len(names), 46, 90) and np.isfinite(fx["y_block"]).all()
+        assert (fx["y_std"] > 0).all() and float(fx["oracle_seconds"]) > 1.0

@@ -1,0 +1,58 @@
+"""Full-size (BASELINE.json shape, 721x1440) sampled fixtures from ONE real oracle step per model:
+
+    python tools/make_golden_full.py pangu      # ~5 min on 8 host threads, ~20 GB RAM
+    python tools/make_golden_full.py sfno       # E=384, L=8: ~10 min
+
+writes tests/golden/{pangu,sfno}_721x1440_seed0.npz holding, per channel,
+  y_sample   y[:, ::16, ::16]                   point values (46 x 90)
+  y_block    16x16 block means of y[:, :720]    every pixel of rows 0..719 enters exactly one mean (45 x 90)
+  y_last     y[:, 720, ::4]                     the odd last latitude row (padding edge of the patch grid)
+  y_norm, y_mean, y_std                         per-channel L2 norm / mean / standard deviation of the full field
+so that tests/test_fullsize_gpu.py and bench.py can compare a full-size CUDA step with the oracle without
+re-running it (the GPU box has no /root/reference and its minutes are budgeted).  Seeded weights and IC are
+regenerated bit-identically from skyrim_b200/weights.py; x0_sample pins that.
+"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+
+
+def summarise(y):
+    y = np.asarray(y, dtype=np.float64)
+    blk = y[:, :720].reshape(y.shape[0], 45, 16, 90, 16).mean(axis=(2, 4))
+    return dict(y_sample=y[:, ::16, ::16].astype(np.float32), y_block=blk.astype(np.float32),
+                y_last=y[:, 720, ::4].astype(np.float32), y_norm=np.sqrt((y ** 2).sum(axis=(1, 2))),
+                y_mean=y.mean(axis=(1, 2)), y_std=y.std(axis=(1, 2)))
+
+
+def main(which):
+    out = os.path.join(ROOT, "tests", "golden")
+    t0 = time.time()
+    if which == "pangu":
+        from skyrim_b200.config import PANGU_CHANNELS, pangu_full
+        from skyrim_b200.weights import make_pangu_weights, synthetic_state
+        from oracle.pangu_ref import PanguRef
+        cfg = pangu_full()
+        w = make_pangu_weights(cfg, 0)
+        x0 = synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0)
+        y = PanguRef(cfg, w, torch.float32).step(x0).numpy()
+    else:
+        from skyrim_b200.config import FCNV2_CHANNELS, sfno_full
+        from skyrim_b200.weights import make_sfno_weights, synthetic_state
+        from oracle.sfno_ref import SFNORef
+        cfg = sfno_full()
+        w = make_sfno_weights(cfg, 0)
+        x0 = synthetic_state(FCNV2_CHANNELS, cfg.nlat, cfg.nlon, 0)
+        y = SFNORef(cfg, w, torch.float32).step(x0).numpy()
+    d = summarise(y)
+    d["x0_sample"] = x0[:, ::64, ::64].astype(np.float32)
+    d["oracle_seconds"] = np.float64(time.time() - t0)
+    d["oracle_threads"] = np.int64(torch.get_num_threads())
+    path = os.path.join(out, f"{which}_721x1440_seed0.npz")
+    np.savez_compressed(path, **d)
+    print("wrote", path, os.path.getsize(path), "bytes;", f"{time.time() - t0:.1f} s")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
