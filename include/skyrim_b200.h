@@ -91,6 +91,11 @@ int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batc
 int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* workspace,
                          int32_t batch, void* stream);
 
+/* Debug switches of a handle (tests only; never read from the environment): "stop_after" = n makes step() return after
+ * stage n (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3; 99 = run the whole step) so that
+ * sky_model_debug_copy can read the intermediate token buffers. */
+int sky_model_debug_set(sky_model_t* m, const char* key, int64_t value);
+
 /* x[m, c, :, :] += amp * sigma[c] * N(0,1), Philox4x32-10 keyed by (seed, member0 + m):
  * perturbed-IC ensemble members (new functionality; the reference's only perturbation
  * helper is the single-point edit at models/utils.py:70-92). */

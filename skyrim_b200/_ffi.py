@@ -11,6 +11,9 @@ import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libskyrim_b200.so"
+# development build (-DSKY_EXPERIMENTS: CUDA-core reference GEMM, single-CTA kernel variants, timing-experiment
+# switches).  Never loaded unless a test asks for it with lib("dev") / SKYRIM_B200_LIB=dev.
+DEV_LIB_PATH = Path(__file__).resolve().parent / "libskyrim_b200_dev.so"
 
 SKY_MODEL_PANGU6 = 1
 SKY_MODEL_SFNO73 = 2
@@ -47,6 +50,7 @@ EXPORTS = {
                                  C.c_void_p]),
     "sky_model_debug_copy": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32,
                                        C.c_void_p]),
+    "sky_model_debug_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sky_perturb_ic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int64, C.c_void_p]),
     "sky_model_profile_begin": (C.c_int, [C.c_void_p, C.c_uint64]),
@@ -57,24 +61,27 @@ EXPORTS = {
     "sky_model_destroy": (C.c_int, [C.c_void_p]),
 }
 
-_lib = None
+_libs = {}
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        if not LIB_PATH.exists():
-            raise SkyError(f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; "
+def lib(variant: str | None = None) -> C.CDLL:
+    """The product library (default) or, for tests that bisect against the reference kernels, the dev build."""
+    variant = variant or os.environ.get("SKYRIM_B200_LIB", "prod")
+    if variant not in _libs:
+        path = DEV_LIB_PATH if variant == "dev" else LIB_PATH
+        if not path.exists():
+            raise SkyError(f"{path} not found — build it with `python -c 'import __graft_entry__ as g; "
                            f"g.build()'` (there is no CPU fallback)")
-        _lib = C.CDLL(os.fspath(LIB_PATH))
+        L = C.CDLL(os.fspath(path))
         for name, (res, args) in EXPORTS.items():
-            fn = getattr(_lib, name)
+            fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", L=None):
     if rc != 0:
-        msg = lib().sky_last_error()
+        msg = (L or lib()).sky_last_error()
         raise SkyError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

@@ -31,10 +31,12 @@ struct ParamView {
 struct Engine {
   int device = 0;
   int num_sms = 148;
-  float* arena = nullptr;  // resident fp32 copy of the weight arena
+  float* arena = nullptr;  // fp32 copy of the weight arena: alive during load_arena() only (freed after repacking)
   uint64_t arena_floats = 0;
   std::map<std::string, ParamView> params;
+  std::vector<void*> kept;  // small persistent fp32 tensors (biases, norm vectors, masks): copies that outlive the arena
   bool loaded = false;
+  int stop_after = 99;      // debug tap (sky_model_debug_set "stop_after"): return from step() after stage n
 
   // optional per-kernel timing: events are recorded around launches whose tag is in prof_mask
   uint64_t prof_mask = 0;
@@ -53,13 +55,15 @@ struct Engine {
   virtual ~Engine();
   int load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,
                  int on_device, cudaStream_t st);
-  const float* param(const char* name, uint64_t expect_count);  // nullptr + error if missing / wrong size
+  const float* param(const char* name, uint64_t expect_count);  // nullptr + error if missing / wrong size; valid during prepare() only
+  const float* keep(const char* name, uint64_t expect_count, cudaStream_t st);  // persistent device copy of a parameter
 
   virtual int prepare(cudaStream_t st) = 0;  // repack weights after load_arena
   virtual size_t workspace_bytes(int batch) const = 0;
   virtual int step(const float* x_in, float* x_out, int batch, void* ws, size_t ws_bytes, cudaStream_t st) = 0;
   virtual int debug_copy(const char* what, float* dst, uint64_t max_floats, void* ws, int batch,
                          cudaStream_t st) = 0;
+  virtual int debug_set(const char* key, long long value);
 };
 
 Engine* make_pangu_engine(const sky_pangu_config_t& cfg, int device);

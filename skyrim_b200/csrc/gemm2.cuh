@@ -205,11 +205,8 @@ int launch_gemm2(const AImage& A, const Epi& epi, const uint8_t* Wimg, long long
                  cudaStream_t st) {
   using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
   auto kern = k_gemm2<Epi, BLOCK_N, EPI_WARPS>;
-  static bool configured = false;
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int num_m_tiles = (int)((M + G2_BLOCK_M - 1) / G2_BLOCK_M);
   const int num_n_tiles = N / BLOCK_N;
   const int tiles = num_m_tiles * num_n_tiles;
@@ -264,7 +261,11 @@ struct Epi2F16 {
   static constexpr bool kNeedsBias = false;
   __half* out; int ldo; int nkb; const float* bias;
   const float* gamma = nullptr; const float* beta = nullptr;  // unused (uniform epilogue interface)
+#ifdef SKY_EXPERIMENTS
   int exp = 0;  // timing experiments only (results invalid): 2 = no global stores
+#else
+  static constexpr int exp = 0;
+#endif
   // head_major (row-major mode only): column block j of 32 goes to out[j][row][0..32), i.e. (part, head, token, 32) for
   // the QKV projection.  A warp store then covers 8 consecutive tokens x 64 B = 512 contiguous bytes instead of 8
   // half lines 2*ldo bytes apart, and the attention kernel reads 64-byte rows that are contiguous along longitude.
@@ -336,7 +337,11 @@ struct Epi2F32Img {
   float* x; int ldx;            // fp32 row-major
   uint8_t* img; int nkb;        // fp16 image of the same rows (may be null)
   const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
+#ifdef SKY_EXPERIMENTS
   int exp = 0;  // timing experiments only (results invalid): 1 = no residual loads, 2 = no fp32 stores, 4 = no image stores
+#else
+  static constexpr int exp = 0;
+#endif
   // Pull this warp's residual rows into L2 ahead of time.  A register-destination prefetch does
   // not work here: tcgen05.wait::ld also waits for the thread's outstanding global loads, so
   // every TMEM read in run() would expose the full HBM latency (profiles/r1_mlp.md).

@@ -157,11 +157,8 @@ int launch_gemm_batched(const AOperand& A, const Epi& epi, const uint8_t* Wimg, 
                         int N, int Ktot, int batches, int num_sms, cudaStream_t st) {
   using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
   auto kern = k_gemm_batched<Epi, BLOCK_N, EPI_WARPS>;
-  static bool configured = false;
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int num_m_tiles = (int)((M + G2_BLOCK_M - 1) / G2_BLOCK_M);
   const int num_n_tiles = N / BLOCK_N;
   const long long tiles = (long long)num_m_tiles * num_n_tiles * batches;

@@ -200,15 +200,16 @@ int launch_gemm_pair(const uint8_t* Aimg, const Epi& epi, const uint8_t* Wimg, l
                      cudaStream_t st) {
   using Cfg = GPairCfg<C>;
   auto kern = k_gemm_pair<Epi, C>;
-  static bool configured = false;
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);
   const int supers = (tiles + 1) / 2;
   const int pairs = supers < num_sms / 2 ? supers : num_sms / 2;
+#ifdef SKY_EXPERIMENTS
   static const int expflags = getenv("SKY_QKV_EXP") ? atoi(getenv("SKY_QKV_EXP")) : 0;  // timing experiments only
+#else
+  constexpr int expflags = 0;
+#endif
   kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(Aimg, epi, Wimg, M, tiles, N / Cfg::NT, expflags);
   SKY_CUDA_OK(cudaGetLastError());
   return 0;

@@ -182,11 +182,8 @@ int launch_gemm_tc(const Prod& prod, const Epi& epi, const uint8_t* Wimg, long l
                    int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   auto kern = k_gemm_tc<Prod, Epi, BLOCK_N>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int num_m_tiles = (int)((M + TC_BLOCK_M - 1) / TC_BLOCK_M);
   const int num_n_tiles = N / BLOCK_N;
   const int tiles = num_m_tiles * num_n_tiles;

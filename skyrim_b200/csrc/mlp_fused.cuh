@@ -305,11 +305,8 @@ int launch_mlp_fused(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W
   if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 256 * 8);
   using Cfg = MlpCfg<C>;
   auto kern = k_mlp_fused<C>;
-  static bool configured = false;
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);
   const int grid = tiles < num_sms ? tiles : num_sms;
   static const int expflags = getenv("SKY_MLP_EXP") ? atoi(getenv("SKY_MLP_EXP")) : 0;  // timing experiments only

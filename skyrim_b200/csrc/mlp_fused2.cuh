@@ -69,8 +69,13 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
                  const EpiLnRes epi,   // x (fp32), xh out image, b2, gamma, beta
                  const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
                  const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
-                 const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg) {
+                 const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg_in) {
   using Cfg = Mlp2Cfg<C>;
+#ifdef SKY_EXPERIMENTS
+  long long* const dbg = dbg_in;      // cycle accounting of the role warps (dev build, SKY_MLP_DBG)
+#else
+  constexpr long long* dbg = nullptr;  // product build: every timer below folds away
+#endif
   long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define SKY_T2(i, stmt) do { long long _t0 = dbg ? clock64() : 0; stmt; if (dbg) tacc[i] += clock64() - _t0; } while (0)
   const long long t_begin = dbg ? clock64() : 0;
@@ -339,19 +344,19 @@ template <int C>
 int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W1img,
                           const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
+#ifdef SKY_EXPERIMENTS
   static int dbg_runs = 0;
   if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 256 * 8);
+#endif
   using Cfg = Mlp2Cfg<C>;
   auto kern = k_mlp_fused_pair<C>;
-  static bool configured = false;
-  if (!configured) {
-    SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
+  if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);
   const int supers = (tiles + 1) / 2;
   const int pairs = supers < num_sms / 2 ? supers : num_sms / 2;
   kern<<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(xh_in, epi, W1img, W2img, b1, M, tiles, dbg);
+#ifdef SKY_EXPERIMENTS
   if (dbg && dbg_runs < 2) {
     ++dbg_runs;
     cudaDeviceSynchronize();
@@ -362,6 +367,7 @@ int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiLnRes& epi, const uint8
              (supers + pairs - 1) / pairs, e[15], e[0], e[1], e[2], e[3], e[4], m[0], m[1], m[2], m[3], m[4], m[7]);
     }
   }
+#endif
   SKY_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -12,15 +12,19 @@
 #include <cstring>
 #include <vector>
 
-#include "attention.cuh"
+#include "attention_tc.cuh"
 #include "engine.h"
 #include "gemm2.cuh"
-#include "gemm2_ref.cuh"
-#include "gemm_ref.cuh"
 #include "gemm_tc.cuh"
-#include "mlp_fused.cuh"
 #include "mlp_fused2.cuh"
 #include "gemm_pair.cuh"
+#ifdef SKY_EXPERIMENTS
+// development build only (libskyrim_b200_dev.so): CUDA-core reference GEMMs under the same epilogues, the single-CTA
+// kernel variants and the result-invalidating timing switches.  None of this is compiled into the product library.
+#include "gemm2_ref.cuh"
+#include "gemm_ref.cuh"
+#include "mlp_fused.cuh"
+#endif
 
 namespace sky {
 
@@ -138,6 +142,8 @@ struct PanguEngine : Engine {
   bool mlp_pair192 = true, mlp_pair384 = true;
   bool qkv_pair = true;     // SKY_QKV=1cta selects k_gemm2 for the QKV projection (A/B timing)
   bool prof_split = false;  // SKY_PROF_SPLIT: report the C=384 MLP launches under the (otherwise unused) fc2 tag
+  int exp_qkv = 0, exp_ln = 0;  // dev build only: result-invalidating timing experiments
+  bool attn_ref = false;        // dev build only (SKY_ATTN=ref): CUDA-core reference attention on the same window image
   std::vector<void*> owned;
   GemmW embed_u, embed_s, down, up1, up2, rec;
   std::vector<BlockW> blocks[4];
@@ -160,6 +166,7 @@ struct PanguEngine : Engine {
     int H = (c.nlat + 3) / 4, W = c.nlon / 4;
     g1 = mk(H, W, c.dim, c.heads[0]);
     g2 = mk((H + 1) / 2, W / 2, 2 * c.dim, c.heads[1]);
+#ifdef SKY_EXPERIMENTS   // read once, at creation; the product library reads no environment variable at all
     const char* e = getenv("SKY_GEMM");
     use_ref = e && !strcmp(e, "ref");
     const char* m = getenv("SKY_MLP");
@@ -169,6 +176,11 @@ struct PanguEngine : Engine {
     prof_split = getenv("SKY_PROF_SPLIT") != nullptr;
     const char* qv = getenv("SKY_QKV");
     qkv_pair = !(qv && !strcmp(qv, "1cta"));
+    exp_qkv = getenv("SKY_QKV_EXP") ? atoi(getenv("SKY_QKV_EXP")) : 0;
+    exp_ln = getenv("SKY_LN_EXP") ? atoi(getenv("SKY_LN_EXP")) : 0;
+    const char* at = getenv("SKY_ATTN");
+    attn_ref = at && !strcmp(at, "ref");
+#endif
   }
   ~PanguEngine() override {
     for (void* p : owned) cudaFree(p);
@@ -206,14 +218,14 @@ struct PanguEngine : Engine {
 
   int prepare(cudaStream_t st) override {
     const int C = cfg.dim;
-#define P(dst, name, cnt) if (!((dst) = param(name, (uint64_t)(cnt)))) return SKY_ERR_ARG;
+#define P(dst, name, cnt) if (!((dst) = keep(name, (uint64_t)(cnt), st))) return SKY_ERR_ARG;   // persistent copies
     P(mean, "norm.mean", nch); P(stdv, "norm.std", nch);
     P(masks, "const.masks", 3LL * cfg.nlat * cfg.nlon);
     P(embed_u_b, "embed.upper.b", C); P(embed_s_b, "embed.surf.b", C);
     P(down_g, "down.ln.g", 4 * C); P(down_b, "down.ln.b", 4 * C);
     P(up_g, "up.ln.g", C); P(up_b, "up.ln.b", C);
-    const float *ru, *rs;
-    P(ru, "recover.upper.b", 5); P(rs, "recover.surf.b", 4);
+    const float *ru = param("recover.upper.b", 5), *rs = param("recover.surf.b", 4);
+    if (!ru || !rs) return SKY_ERR_ARG;
     rec_b = dalloc<float>(16);
     if (!rec_b) return SKY_ERR_NOMEM;
     SKY_CUDA_OK(cudaMemcpyAsync(rec_b, ru, 5 * 4, cudaMemcpyDeviceToDevice, st));
@@ -240,24 +252,27 @@ struct PanguEngine : Engine {
         if ((rc = pack(b.proj, N("proj.w"), c, c, c, false, st))) return rc;
         if ((rc = pack(b.fc1, N("fc1.w"), 4 * c, c, 192, false, st))) return rc;
         if ((rc = pack(b.fc2, N("fc2.w"), c, 4 * c, c, false, st))) return rc;
+#ifdef SKY_EXPERIMENTS
         const int hc = (c == 192 ? mlp_pair192 : mlp_pair384) ? 128 : (c == 192 ? MlpCfg<192>::HC : MlpCfg<384>::HC);
+#else
+        const int hc = 128;   // hidden-chunk width of k_mlp_fused_pair
+#endif
         if ((rc = pack(b.fc1f, N("fc1.w"), 4 * c, c, hc, false, st))) return rc;
         P(b.qkv_b, N("qkv.b"), 3 * c); P(b.proj_b, N("proj.b"), c);
         P(b.fc1_b, N("fc1.b"), 4 * c); P(b.fc2_b, N("fc2.b"), c);
         P(b.ln1_g, N("ln1.g"), c); P(b.ln1_b, N("ln1.b"), c);
         P(b.ln2_g, N("ln2.g"), c); P(b.ln2_b, N("ln2.b"), c);
-        const float* bt;
-        long long tot = (long long)ATT_TABLE * n_type * heads;
-        P(bt, N("bias_table"), tot);
+        long long tot = (long long)AT_TABLE * n_type * heads;
+        const float* bt = param(N("bias_table"), (uint64_t)tot);   // transient: repacked below
+        if (!bt) return SKY_ERR_ARG;
         b.bias_tab = dalloc<__half>((size_t)tot);
         if (!b.bias_tab) return SKY_ERR_NOMEM;
-        k_pack_bias_table<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(bt, b.bias_tab, ATT_TABLE, n_type, heads);
+        k_pack_bias_table<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(bt, b.bias_tab, AT_TABLE, n_type, heads);
         count_launch();
       }
     }
 #undef P
     SKY_CUDA_OK(cudaGetLastError());
-    SKY_CUDA_OK(cudaFuncSetAttribute(k_window_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     SKY_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
   }
@@ -266,7 +281,7 @@ struct PanguEngine : Engine {
   struct Ws {
     float *x1, *x2, *scratch;
     uint8_t *x1h, *skiph, *x2h, *atth, *hidh;
-    __half* qkv;
+    uint8_t* qkv;
     size_t x1h_bytes;
     size_t total;
   };
@@ -284,8 +299,9 @@ struct PanguEngine : Engine {
     w.x1h = (uint8_t*)take(w.x1h_bytes);
     w.skiph = (uint8_t*)take(w.x1h_bytes);
     w.x2h = (uint8_t*)take(t2 * (2 * C / 64) * G2_A_BYTES);
-    size_t qkv_el = (size_t)R1 * 3 * C > (size_t)R2 * 6 * C ? (size_t)R1 * 3 * C : (size_t)R2 * 6 * C;
-    w.qkv = (__half*)take(qkv_el * 2);
+    // q | k | v window images (attention_tc.cuh): one 144-row x 128-byte tile per (member, window, head pair) and part
+    const size_t wt1 = (size_t)B * g1.nWin * (g1.heads / 2), wt2 = (size_t)B * g2.nWin * (g2.heads / 2);
+    w.qkv = (uint8_t*)take(3 * (wt1 > wt2 ? wt1 : wt2) * AT_TILE_B);
     size_t att_b = t1 * (C / 64) > t2 * (2 * C / 64) ? t1 * (C / 64) : t2 * (2 * C / 64);
     w.atth = (uint8_t*)take(att_b * G2_A_BYTES);
     size_t hid_b = t1 * (4 * C / 64) > t2 * (8 * C / 64) ? t1 * (4 * C / 64) : t2 * (8 * C / 64);
@@ -304,10 +320,13 @@ struct PanguEngine : Engine {
     if (w.BN != BN) { set_error("internal: weight packed for BLOCK_N=%d used with %d", w.BN, BN); return SKY_ERR_STATE; }
     int rc;
     prof_begin(tag, st);
+#ifdef SKY_EXPERIMENTS
     if (use_ref) {
       count_launch(2);
       rc = launch_gemm2_ref<Epi, BN>(A, epi, w.plain, scratch, M, w.N, w.Kp, st);
-    } else {
+    } else
+#endif
+    {
       count_launch();
       rc = launch_gemm2<Epi, BN, EW>(A, epi, w.img, M, w.N, w.Kp, num_sms, st);
     }
@@ -319,10 +338,13 @@ struct PanguEngine : Engine {
   int gemm_prod(int tag, const Prod& prod, const Epi& epi, const GemmW& w, long long M, float* scratch, cudaStream_t st) {
     int rc;
     prof_begin(tag, st);
+#ifdef SKY_EXPERIMENTS
     if (use_ref) {
       count_launch(2);
       rc = launch_gemm_ref(prod, epi, w.plain, scratch, M, w.N, w.Kp, BN, st);
-    } else {
+    } else
+#endif
+    {
       count_launch();
       rc = launch_gemm_tc<Prod, Epi, BN>(prod, epi, w.img, M, w.N, w.Kp, num_sms, st);
     }
@@ -334,57 +356,61 @@ struct PanguEngine : Engine {
     const int C = g.C, nkb = C / 64;
     const long long R = (long long)B * g.T;
     int rc;
-    {  // QKV projection on natural-order tokens
+    const int pairs = g.heads / 2;
+    const long long part_stride = (long long)B * g.nWin * pairs * AT_TILE_B;
+    {  // QKV projection: natural-order tokens in, window image out (windowing / shift / padding applied by the epilogue)
       AImage A{xh, xh, nkb, 0};
-      Epi2F16<false, false> e{ws.qkv, 3 * C, 0, b.qkv_b};
-      static const int qkv_exp = getenv("SKY_QKV_EXP") ? atoi(getenv("SKY_QKV_EXP")) : 0;  // timing experiments only
-      e.exp = qkv_exp;
-      e.head_major = 1;   // (3, heads, tokens, 32): what k_window_attention reads
+      EpiQkvWin e{ws.qkv, part_stride, b.qkv_b, g, roll, C, pairs};
+#ifdef SKY_EXPERIMENTS
+      e.exp = exp_qkv;
       if (use_ref || !qkv_pair) {
         if ((rc = gemm2<192, 8>(KT_QKV, A, e, b.qkv, R, ws.scratch, st))) return rc;
-      } else {  // A-stationary CTA-pair kernel: a third of the L2 traffic of the tile-streaming kernel
+      } else
+#endif
+      {  // A-stationary CTA-pair kernel: a third of the L2 traffic of the tile-streaming kernel
         prof_begin(KT_QKV, st);
         count_launch();
-        rc = C == 192 ? launch_gemm_pair<Epi2F16<false, false>, 192>(xh, e, b.qkv.img, R, 3 * C, num_sms, st)
-                      : launch_gemm_pair<Epi2F16<false, false>, 384>(xh, e, b.qkv.img, R, 3 * C, num_sms, st);
+        rc = C == 192 ? launch_gemm_pair<EpiQkvWin, 192>(xh, e, b.qkv.img, R, 3 * C, num_sms, st)
+                      : launch_gemm_pair<EpiQkvWin, 384>(xh, e, b.qkv.img, R, 3 * C, num_sms, st);
         prof_end(KT_QKV, st);
         if (rc) return rc;
       }
+      if (g.Hp > g.H) {   // latitude-padding tokens (x = 0): their q, k, v rows are the projection's bias
+        const long long total = 3LL * B * g.Z * (g.Hp - g.H) * g.W * pairs * 8;
+        prof_begin(KT_QKV, st);
+        k_qkv_fill_pad<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.qkv, part_stride, b.qkv_b, g, roll, B, pairs, C, total);
+        prof_end(KT_QKV, st);
+        count_launch();
+        SKY_CUDA_OK(cudaGetLastError());
+      }
     }
     {
-      dim3 grid(g.heads, (unsigned)g.nWin, (unsigned)B);
+      AttnArgs a{ws.qkv, part_stride, ws.atth, nkb, b.bias_tab, g, roll, B, pairs,
+                 rsqrtf(32.f) * 1.4426950408889634f, cfg.mask_value * 1.4426950408889634f, (long long)B * g.nWin * pairs};
       prof_begin(KT_ATTN, st);
-      k_window_attention<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(ws.qkv, ws.atth, nkb, b.bias_tab, b.qkv_b, g, roll,
-                                                                  rsqrtf(32.f), cfg.mask_value, R);
-      prof_end(KT_ATTN, st);
       count_launch();
-      SKY_CUDA_OK(cudaGetLastError());
+#ifdef SKY_EXPERIMENTS
+      if (attn_ref) {
+        k_window_attention_ref<<<dim3((unsigned)a.items, 2), WIN_TOK, 0, st>>>(a);
+        rc = cudaGetLastError() == cudaSuccess ? 0 : SKY_ERR_CUDA;
+      } else
+#endif
+        rc = launch_window_attention_tc(a, num_sms, st);
+      prof_end(KT_ATTN, st);
+      if (rc) return rc;
     }
     {  // projection + LayerNorm + residual
       AImage A{ws.atth, ws.atth, nkb, 0};
       EpiLnRes e{x, C, xh, nkb, b.proj_b, b.ln1_g, b.ln1_b, cfg.ln_eps};
-      static const int ln_exp = getenv("SKY_LN_EXP") ? atoi(getenv("SKY_LN_EXP")) : 0;  // timing experiments only
-      e.exp = ln_exp;
+#ifdef SKY_EXPERIMENTS
+      e.exp = exp_ln;
+#endif
       rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
                     : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
       if (rc) return rc;
     }
-    if (!use_ref) {  // fused MLP: fc1 + GELU + fc2 + LayerNorm + residual, hidden stays on the SM
-      EpiLnRes e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
-      static const int ln_exp2 = getenv("SKY_LN_EXP") ? atoi(getenv("SKY_LN_EXP")) : 0;  // timing experiments only
-      e2.exp = ln_exp2;
-      const KTag tag = (prof_split && C == 384) ? KT_FC2 : KT_MLP;
-      prof_begin(tag, st);
-      count_launch();
-      if (C == 192)
-        rc = mlp_pair192 ? launch_mlp_fused_pair<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
-                         : launch_mlp_fused<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
-      else
-        rc = mlp_pair384 ? launch_mlp_fused_pair<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
-                         : launch_mlp_fused<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
-      prof_end(tag, st);
-      if (rc) return rc;
-    } else {  // two plain GEMMs through an HBM-resident hidden image (reference path only)
+#ifdef SKY_EXPERIMENTS
+    if (use_ref) {  // two plain GEMMs through an HBM-resident hidden image (reference path only)
       AImage A{xh, xh, nkb, 0};
       Epi2F16<true, true> e{reinterpret_cast<__half*>(ws.hidh), 0, 4 * nkb, b.fc1_b};
       if ((rc = gemm2<192, 8>(KT_FC1, A, e, b.fc1, R, ws.scratch, st))) return rc;
@@ -392,6 +418,27 @@ struct PanguEngine : Engine {
       EpiLnRes e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
       rc = C == 192 ? gemm2<192, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st)
                     : gemm2<384, 8>(KT_FC2, A2, e2, b.fc2, R, ws.scratch, st);
+      return rc;
+    }
+#endif
+    {  // fused MLP: fc1 + GELU + fc2 + LayerNorm + residual, hidden stays on the SM
+      EpiLnRes e2{x, C, xh, nkb, b.fc2_b, b.ln2_g, b.ln2_b, cfg.ln_eps};
+      KTag tag = KT_MLP;
+#ifdef SKY_EXPERIMENTS
+      e2.exp = exp_ln;
+      if (prof_split && C == 384) tag = KT_FC2;
+#endif
+      prof_begin(tag, st);
+      count_launch();
+#ifdef SKY_EXPERIMENTS
+      if (!(C == 192 ? mlp_pair192 : mlp_pair384))
+        rc = C == 192 ? launch_mlp_fused<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
+                      : launch_mlp_fused<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
+      else
+#endif
+        rc = C == 192 ? launch_mlp_fused_pair<192>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st)
+                      : launch_mlp_fused_pair<384>(xh, e2, b.fc1f.img, b.fc2.img, b.fc1_b, R, num_sms, st);
+      prof_end(tag, st);
       if (rc) return rc;
     }
     return 0;
@@ -404,10 +451,9 @@ struct PanguEngine : Engine {
     const int C = cfg.dim, HW = g1.H * g1.W, nzt = g1.Z - 1;
     const long long R1 = (long long)B * g1.T, R2 = (long long)B * g2.T;
     int rc;
-    // test tap: SKY_STOP_AFTER=<stage> returns early so debug_copy can read the token buffers
-    // (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3)
-    const char* stop_env = getenv("SKY_STOP_AFTER");
-    const int stop = stop_env ? atoi(stop_env) : 99;
+    // test tap (sky_model_debug_set "stop_after"): return early so that debug_copy can read the token buffers
+    // (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3; default 99 = whole step)
+    const int stop = stop_after;
     // ---- patch embedding ----
     {
       long long M = (long long)B * nzt * HW;

@@ -301,14 +301,16 @@ struct SfnoEngine : Engine {
   int prepare(cudaStream_t st) override {
     if (E % 64) { set_error("embed must be a multiple of 64"); return SKY_ERR_ARG; }
     int rc;
+    // P: transient view into the fp32 arena (repacked below, the arena is freed after prepare); KEEP: persistent copy
 #define P(dst, name, cnt) if (!((dst) = param(name, (uint64_t)(cnt)))) return SKY_ERR_ARG;
+#define KEEP(dst, name, cnt) if (!((dst) = keep(name, (uint64_t)(cnt), st))) return SKY_ERR_ARG;
     const float *w_e1, *w_e2, *w_d1, *w_d2, *pos, *t;
-    P(mean, "norm.mean", Cin); P(stdv, "norm.std", Cin);
-    P(w_e1, "enc.fc1.w", (long long)E * Cin); P(enc1_b, "enc.fc1.b", E);
-    P(w_e2, "enc.fc2.w", (long long)E * E); P(enc2_b, "enc.fc2.b", E);
+    KEEP(mean, "norm.mean", Cin); KEEP(stdv, "norm.std", Cin);
+    P(w_e1, "enc.fc1.w", (long long)E * Cin); KEEP(enc1_b, "enc.fc1.b", E);
+    P(w_e2, "enc.fc2.w", (long long)E * E); KEEP(enc2_b, "enc.fc2.b", E);
     P(pos, "pos_embed", (long long)E * P1);
-    P(w_d1, "dec.fc1.w", (long long)E * (E + Cin)); P(dec1_b, "dec.fc1.b", E);
-    P(w_d2, "dec.fc2.w", (long long)Cin * E); P(dec2_b, "dec.fc2.b", Cin);
+    P(w_d1, "dec.fc1.w", (long long)E * (E + Cin)); KEEP(dec1_b, "dec.fc1.b", E);
+    P(w_d2, "dec.fc2.w", (long long)Cin * E); KEEP(dec2_b, "dec.fc2.b", Cin);
     const int CinP = pad_to(Cin, 64);
     if ((rc = pack_w(enc1, w_e1, 0, E, Cin, E, bn_point(E), 1, 0, Cin, 1, st))) return rc;
     if ((rc = pack_w(enc2, w_e2, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
@@ -341,18 +343,19 @@ struct SfnoEngine : Engine {
       char nm[96];
       auto N = [&](const char* s) { snprintf(nm, sizeof nm, "blk%d.%s", i, s); return nm; };
       const float* w;
-      P(b.n0g, N("norm0.g"), E); P(b.n0b, N("norm0.b"), E); P(b.n1g, N("norm1.g"), E); P(b.n1b, N("norm1.b"), E);
+      KEEP(b.n0g, N("norm0.g"), E); KEEP(b.n0b, N("norm0.b"), E); KEEP(b.n1g, N("norm1.g"), E); KEEP(b.n1b, N("norm1.b"), E);
       P(w, N("spec.w"), (long long)lmax * E * E * 2);
       if ((rc = pack_w(b.spec, w, 1, 2 * E, 2 * E, 2 * E, bn_point(2 * E), lmax, 0, 0, 0, st))) return rc;
-      P(w, N("inner.w"), (long long)E * E); P(b.inner_b, N("inner.b"), E);
+      P(w, N("inner.w"), (long long)E * E); KEEP(b.inner_b, N("inner.b"), E);
       if ((rc = pack_w(b.inner, w, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
       const int Hd = cfg.mlp_ratio * E;
-      P(w, N("fc1.w"), (long long)Hd * E); P(b.fc1_b, N("fc1.b"), Hd);
+      P(w, N("fc1.w"), (long long)Hd * E); KEEP(b.fc1_b, N("fc1.b"), Hd);
       if ((rc = pack_w(b.fc1, w, 0, Hd, E, Hd, bn_point(Hd), 1, 0, E, 1, st))) return rc;
-      P(w, N("fc2.w"), (long long)E * Hd); P(b.fc2_b, N("fc2.b"), E);
+      P(w, N("fc2.w"), (long long)E * Hd); KEEP(b.fc2_b, N("fc2.b"), E);
       if ((rc = pack_w(b.fc2, w, 0, E, Hd, E, bn_point(E), 1, 0, Hd, 1, st))) return rc;
     }
 #undef P
+#undef KEEP
     // positional embedding in pixel-major order
     pos_pm = dalloc<float>((size_t)P1 * E);
     if (!pos_pm) return SKY_ERR_NOMEM;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace sky {
 
 // ---------------------------------------------------------------------------------------
@@ -20,6 +22,29 @@ void set_error(const char* fmt, ...);
       return -2;                                                                           \
     }                                                                                      \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(function, device) attribute: opt in once per device the
+// function is launched on (`mask` is the launch site's own static bit set, one bit per device ordinal).
+inline int smem_opt_in(std::atomic<uint64_t>& mask, const void* kern, int bytes) {
+  int dev = 0;
+  SKY_CUDA_OK(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_acquire) & bit) return 0;
+  SKY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  mask.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+// RAII: make `dev` current for the duration of a C-ABI call and restore the caller's device afterwards
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---------------------------------------------------------------------------------------
 // small device utilities

@@ -52,14 +52,14 @@ def _sfno_cfg_c(cfg: SFNOConfig) -> _ffi.SFNOConfigC:
 class StepEngine:
     """One 6-h step operator resident on one GPU."""
 
-    def __init__(self, cfg, device: int = 0):
+    def __init__(self, cfg, device: int = 0, lib: str | None = None):
         import torch
         if not torch.cuda.is_available():
             raise _ffi.SkyError("skyrim_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg = cfg
         self.device = device
         self.torch = torch
-        L = _ffi.lib()
+        L = self._L = _ffi.lib(lib)
         if isinstance(cfg, PanguConfig):
             kind, cc = _ffi.SKY_MODEL_PANGU6, _pangu_cfg_c(cfg)
         elif isinstance(cfg, SFNOConfig):
@@ -80,7 +80,7 @@ class StepEngine:
 
     def load_arena(self, arena, manifest):
         """``arena``: host numpy fp32 array, or a CUDA torch tensor (e.g. after a broadcast)."""
-        L = _ffi.lib()
+        L = self._L
         torch = self.torch
         st = torch.cuda.current_stream(self.device).cuda_stream
         if isinstance(arena, np.ndarray):
@@ -94,7 +94,7 @@ class StepEngine:
     # -- stepping --------------------------------------------------------------------------
     def _workspace(self, batch: int):
         if self._ws is None or self._ws_batch < batch:
-            nbytes = _ffi.lib().sky_model_workspace_bytes(self._h, batch)
+            nbytes = self._L.sky_model_workspace_bytes(self._h, batch)
             self._ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=f"cuda:{self.device}")
             self._ws_batch = batch
         return self._ws
@@ -110,7 +110,7 @@ class StepEngine:
             x_out = torch.empty_like(x_in)
         ws = self._workspace(B)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _ffi.check(_ffi.lib().sky_model_step(self._h, x_in.data_ptr(), x_out.data_ptr(), B, ws.data_ptr(),
+        _ffi.check(self._L.sky_model_step(self._h, x_in.data_ptr(), x_out.data_ptr(), B, ws.data_ptr(),
                                              ws.numel(), st), "sky_model_step")
         return x_out
 
@@ -118,9 +118,13 @@ class StepEngine:
         torch = self.torch
         out = torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.device}")
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _ffi.check(_ffi.lib().sky_model_debug_copy(self._h, what.encode(), out.data_ptr(), out.numel(),
+        _ffi.check(self._L.sky_model_debug_copy(self._h, what.encode(), out.data_ptr(), out.numel(),
                                                    self._workspace(batch).data_ptr(), batch, st), "debug_copy")
         return out
+
+    def debug_set(self, key: str, value: int):
+        """test taps (never environment variables): e.g. ``debug_set("stop_after", 3)``"""
+        _ffi.check(self._L.sky_model_debug_set(self._h, key.encode(), int(value)), "debug_set", self._L)
 
     # -- per-kernel-family device timing (CUDA events inside the library) -------------------
     @staticmethod
@@ -134,19 +138,19 @@ class StepEngine:
         for i, n in enumerate(names):
             if tags is None or n in tags:
                 mask |= 1 << i
-        _ffi.check(_ffi.lib().sky_model_profile_begin(self._h, mask), "profile_begin")
+        _ffi.check(self._L.sky_model_profile_begin(self._h, mask), "profile_begin")
 
     def profile_end(self):
         """-> {family: (total_ms, launches)} for the families that ran since profile_begin."""
         names = self.profile_tags()
         ms = (C.c_double * len(names))()
         cnt = (C.c_uint64 * len(names))()
-        _ffi.check(_ffi.lib().sky_model_profile_end(self._h, ms, cnt, len(names)), "profile_end")
+        _ffi.check(self._L.sky_model_profile_end(self._h, ms, cnt, len(names)), "profile_end")
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names) if cnt[i]}
 
     def close(self):
         if getattr(self, "_h", None):
-            _ffi.lib().sky_model_destroy(self._h)
+            self._L.sky_model_destroy(self._h)
             self._h = None
             self._ws = None
 

@@ -31,15 +31,12 @@ def small():
 
 
 def _engine(cfg, w, gemm=None):
+    """gemm="ref": the development library (libskyrim_b200_dev.so, -DSKY_EXPERIMENTS) with the CUDA-core reference
+    GEMMs under the same epilogues; default: the product library, which reads no environment variable."""
     from skyrim_b200.engine import StepEngine
     if gemm:
-        os.environ["SKY_GEMM"] = gemm
-    else:
-        os.environ.pop("SKY_GEMM", None)
-    try:
-        eng = StepEngine(cfg, 0)
-    finally:
-        os.environ.pop("SKY_GEMM", None)
+        return _engine_env(cfg, w, SKY_GEMM=gemm)
+    eng = StepEngine(cfg, 0)
     eng.load_weights(w)
     return eng
 
@@ -90,14 +87,13 @@ def test_stage_parity(small):
     xin = torch.from_numpy(x0)[None].cuda()
     try:
         for i, nm in enumerate(["embed", "layer0", "down", "layer1", "layer2", "up", "layer3"]):
-            os.environ["SKY_STOP_AFTER"] = str(i)
+            eng.debug_set("stop_after", i)
             eng.step(xin)
             which = "tokens2" if nm in ("down", "layer1", "layer2") else "tokens1"
             t = eng.debug_tensor(which, tuple(st[nm].shape)).cpu()
             err = float((t - st[nm]).norm() / st[nm].norm())
             assert err < 2e-3, (nm, err)
     finally:
-        os.environ.pop("SKY_STOP_AFTER", None)
         eng.close()
 
 
@@ -163,11 +159,15 @@ def test_engine_errors_are_loud(small):
 
 
 def _engine_env(cfg, w, **env):
+    """An engine of the DEVELOPMENT library with kernel-selection switches (read once, when the engine is created)."""
+    from skyrim_b200 import _ffi
     from skyrim_b200.engine import StepEngine
+    if not _ffi.DEV_LIB_PATH.exists():
+        pytest.skip("development library not built (make -C skyrim_b200/csrc dev)")
     for k, v in env.items():
         os.environ[k] = v
     try:
-        eng = StepEngine(cfg, 0)   # the kernel selection switches are read when the engine is created
+        eng = StepEngine(cfg, 0, lib="dev")
     finally:
         for k in env:
             os.environ.pop(k, None)
@@ -183,7 +183,7 @@ def test_cta_pair_kernels_agree_with_single_cta_kernels(small):
     from oracle.pangu_ref import rel_err_per_channel
     cfg, w, x0, ref = small
     x = torch.from_numpy(x0)[None].cuda()
-    pair = _engine_env(cfg, w)
+    pair = _engine(cfg, w)
     single = _engine_env(cfg, w, SKY_MLP="1cta", SKY_QKV="1cta")
     yp = pair.step(x)[0].cpu().numpy()
     ys = single.step(x)[0].cpu().numpy()

@@ -18,13 +18,16 @@ ref = PanguRef(cfg, w, torch.float32)
 stages = ref.stages(x0)
 names = ["embed", "layer0", "down", "layer1", "layer2", "up", "layer3"]
 xin = torch.from_numpy(x0)[None].cuda()
-for mode in (sys.argv[3:] or ["ref", "tc"]):
-    os.environ["SKY_GEMM"] = mode
-    eng = StepEngine(cfg, 0)
+# modes: tc = product library; ref = dev library, CUDA-core GEMMs + tcgen05 attention; refattn = dev library,
+# CUDA-core GEMMs + CUDA-core attention (bisects window image / index math from the tensor pipelines)
+for mode in (sys.argv[3:] or ["refattn", "ref", "tc"]):
+    os.environ["SKY_GEMM"] = "ref" if mode.startswith("ref") else "tc"   # read by the development library only
+    os.environ["SKY_ATTN"] = "ref" if mode == "refattn" else "tc"
+    eng = StepEngine(cfg, 0, lib="dev" if mode.startswith("ref") else None)
     eng.load_weights(w)
     print(f"== SKY_GEMM={mode}  grid {nlat}x{nlon}", flush=True)
     for i, nm in enumerate(names):
-        os.environ["SKY_STOP_AFTER"] = str(i)
+        eng.debug_set("stop_after", i)
         try:
             eng.step(xin)
             torch.cuda.synchronize()
@@ -36,7 +39,7 @@ for mode in (sys.argv[3:] or ["ref", "tc"]):
         t = eng.debug_tensor(which, tuple(r.shape)).cpu()
         err = (t - r).norm() / r.norm()
         print(f"  {nm:7s} rel l2 err {err:.3e}  max abs {float((t - r).abs().max()):.3e}  nan={bool(torch.isnan(t).any())}", flush=True)
-    os.environ.pop("SKY_STOP_AFTER")
+    eng.debug_set("stop_after", 99)
     try:
         y = eng.step(xin); torch.cuda.synchronize()
         e = rel_err_per_channel(y[0].cpu().numpy(), stages["out"].numpy())
