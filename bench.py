@@ -3,13 +3,19 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 3            # our arm, 1 GPU
     torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, weak scaling
-    python bench.py --impl reference --steps 5 --warmup 1     # CPU reference arm (the oracle)
+    python bench.py --impl reference --steps 5 --warmup 1     # CPU reference arm
 
-A "step" is one 6-h Pangu step of every member resident on the GPU (``--members-per-gpu``,
-default 1 = config[1] "Pangu 7-day rollout, synthetic IC, 1xB200": the chained device-resident
-rollout).  ``value`` = member-steps per second over all ranks with the state resident in HBM;
-``e2e`` = the same through the reference-facing TimeLoop call with HOST (pinned) input and output
-every step, copies inside the timed region.  One JSON line on rank 0.
+The headline line is BASELINE config 2's step (Pangu 6-h step on the (69,721,1440) state, chained device-resident
+rollout, ``--members-per-gpu`` members per GPU, default 1).  ``value`` = member-steps per second over all ranks with the
+state resident in HBM; ``e2e`` = the same through the reference-facing TimeLoop call with HOST (pinned) input and output
+every step, copies inside the timed region.  The first timed step starts from the seeded synthetic IC, and its output
+is compared with the committed full-size oracle fixture (``verify``): a fast, finite, wrong step fails the run.
+
+The same invocation also measures (sub-records under ``configs``, skipped with ``--only-headline``):
+  config 3  FourCastNet-v2 SFNO 6-h step on (73,721,1440)                     -> configs.sfno
+  config 5  Pangu ensemble with 4 members per GPU (32 members on 8 GPUs)      -> configs.ensemble_m4
+each with ms/step, member-steps/s, per-family roofline fractions, fixture verification, and (N = 1) its e2e figure.
+One JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -26,6 +32,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "6h rollout steps/sec on (69,721,1440); ensemble member-steps/sec @1/2/4/8 GPU"
 UNIT = "member-steps/s"
+VERIFY_TOL = 1e-3      # per-channel relative L2 on the point sample (north star); block means / RMS in sigma units below
+VERIFY_TOL_SIGMA = 5e-3
 
 
 def _peaks():
@@ -33,8 +41,8 @@ def _peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"],
-                    tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
-    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+                    tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -82,224 +90,361 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline: the oracle (restatement of the reference's forward) on the
-# host cores, on a bounded latitude band of the same workload, scaled by the FLOP ratio.
+# CPU reference arm / cpu_baseline.  BASELINE.md section 2: (1) ONNXRuntime-CPU on pangu_weather_6.onnx when both are
+# present on the box, else (2) the oracle (CPU restatement of the reference's forward).  Either way REAL full-size
+# steps on the (69,721,1440) state are timed — no latitude band, no FLOP-fraction extrapolation.
 # --------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int, band_nlat: int):
+def _find_onnx():
+    import glob
+    cands = []
+    w = os.environ.get("SKYRIM_B200_WEIGHTS")
+    if w:
+        cands += [w] if w.endswith(".onnx") else glob.glob(os.path.join(w, "**", "pangu_weather_6.onnx"), recursive=True)
+    for root in ("~/.cache/earth2mip", "~/.cache/modulus", "~/.cache/earth2studio"):
+        cands += glob.glob(os.path.join(os.path.expanduser(root), "**", "pangu_weather_6.onnx"), recursive=True)
+    return next((c for c in cands if os.path.exists(c)), None)
+
+
+def cpu_reference(max_steps: int, budget_s: float = 100.0):
+    """-> dict(value, unit, cores, kind, sample, ms_per_step, steps_timed).  Times at least one and at most `max_steps`
+    real full-size 6-h steps, stopping when the next one would overrun `budget_s`."""
     import numpy as np
-    import torch
-    from oracle.pangu_ref import PanguRef
-    from skyrim_b200.config import PANGU_CHANNELS, pangu_full, pangu_small
-    from skyrim_b200.roofline import pangu_flops
-    from skyrim_b200.weights import make_pangu_weights, synthetic_state
-    # torch's CPU kernels stop scaling (and oversubscribe) beyond a few dozen threads on the
-    # big bench hosts; `cores` reports the threads actually used
-    cores = min(os.cpu_count() or 1, 32)
-    torch.set_num_threads(cores)
-    full, band = pangu_full(), pangu_small(band_nlat, 1440)
-    frac = pangu_flops(band)["total"] / pangu_flops(full)["total"]
-    w = make_pangu_weights(band, 0)
-    x = torch.from_numpy(synthetic_state(PANGU_CHANNELS, band.nlat, band.nlon, 0))
-    ref = PanguRef(band, w)
-    for _ in range(warmup):
-        ref.step(x)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        x = ref.step(x)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    assert bool(torch.isfinite(x).all())
-    return dict(value=frac / dt, unit=UNIT, cores=cores, kind="port", sec_per_sample=dt,
-                sample=(f"oracle (torch fp32, {cores} threads) on a {band_nlat}x1440 latitude band = "
-                        f"{100 * frac:.1f}% of the full step's FLOPs; value = band fraction / seconds"))
+    from skyrim_b200.config import PANGU_CHANNELS, pangu_full
+    from skyrim_b200.weights import synthetic_state
+    cfg = pangu_full()
+    x0 = synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)   # every host thread this process may use
+    onnx_path = None
+    try:
+        import onnxruntime as ort  # noqa: F401
+        onnx_path = _find_onnx()
+    except Exception:
+        ort = None
+    if ort is not None and onnx_path:
+        so = ort.SessionOptions()
+        so.intra_op_num_threads = cores
+        sess = ort.InferenceSession(onnx_path, sess_options=so, providers=["CPUExecutionProvider"])
+        pl = x0[:65].reshape(5, 13, cfg.nlat, cfg.nlon).astype(np.float32)
+        sl = x0[65:].astype(np.float32)
+        step = lambda: sess.run(None, {"input": pl, "input_surface": sl})
+        kind, what = "reference", f"onnxruntime CPUExecutionProvider on {os.path.basename(onnx_path)}, {cores} intra-op threads"
+    else:
+        import torch
+        from oracle.pangu_ref import PanguRef
+        from skyrim_b200.weights import make_pangu_weights
+        torch.set_num_threads(cores)
+        ref = PanguRef(cfg, make_pangu_weights(cfg, 0))
+        xt = torch.from_numpy(x0)
+        state = {"x": xt}
+
+        def step():
+            state["x"] = ref.step(state["x"])
+        kind, what = "port", (f"oracle/pangu_ref.py (torch fp32 CPU restatement of the reference forward; onnxruntime / "
+                              f"pangu_weather_6.onnx not present on this box), {cores} threads")
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max(1, max_steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all + times[-1] > budget_s:
+            break
+    dt = sorted(times)[len(times) // 2]
+    return dict(value=1.0 / dt, unit=UNIT, cores=cores, kind=kind, ms_per_step=1000.0 * dt, steps_timed=len(times),
+                sample=f"{len(times)} real full-size 6-h step(s) on the (69,721,1440) synthetic state, no warm-up, median; {what}")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    band = 49 if total <= 30 else 25
-    cb = cpu_reference(args.steps, args.warmup, band)
+    cb = cpu_reference(args.steps + args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
+            "steps": cb["steps_timed"], "steps_requested": args.steps, "warmup": 0, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Pangu 6-h step, synthetic (69,721,1440) IC, CPU restatement of the reference "
-                                   "forward (onnxruntime / earth2mip are not installable offline)"},
+            "config": {"workload": "Pangu 6-h step, synthetic (69,721,1440) IC, CPU path of the reference (BASELINE config 1); "
+                                   "every timed step is a full-size step — the step count is bounded to ~100 s of CPU work"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from skyrim_b200.config import PANGU_CHANNELS, pangu_full
-    from skyrim_b200.engine import StepEngine, launch_count, pack_arena, perturb_ic
-    from skyrim_b200.roofline import pangu_flops, pangu_state_bytes
-    from skyrim_b200.timeloop import PanguTimeLoop
-    from skyrim_b200.weights import channel_stats, make_pangu_weights, synthetic_state
+class Dist:
+    def __init__(self, args):
+        import torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world}"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    sfno = args.model == "sfno"
-    if sfno:
-        from skyrim_b200.config import FCNV2_CHANNELS as CHANNELS, sfno_full
-        from skyrim_b200.roofline import sfno_flops
-        from skyrim_b200.timeloop import SFNOTimeLoop as Loop
-        from skyrim_b200.weights import make_sfno_weights, sfno_param_shapes, sfno_tables
-        cfg = sfno_full()
-    else:
-        CHANNELS, Loop = PANGU_CHANNELS, PanguTimeLoop
-        cfg = pangu_full()
-    M = args.members_per_gpu
-    # ---- weights: built on rank 0, ONE NCCL broadcast of the fp32 arena, repacked on each device ----
-    if sfno:
-        w = None
-        if rank == 0:
-            w = make_sfno_weights(cfg, 0); w.update(sfno_tables(cfg))
-    else:
-        w = make_pangu_weights(cfg, 0) if rank == 0 else None
-    if world > 1:
-        from skyrim_b200.weights import pangu_param_shapes
-        if sfno:
-            shapes = dict(sfno_param_shapes(cfg))
-            shapes.update({k: v.shape for k, v in sfno_tables(cfg).items()})
-        else:
-            shapes = pangu_param_shapes(cfg)
-        if rank == 0:
-            arena_h, manifest = pack_arena(w)
-            arena = torch.from_numpy(arena_h).to(dev)
-        else:
-            arena_h, manifest = pack_arena({k: np.zeros(s, np.float32) for k, s in shapes.items()})
-            arena = torch.empty(arena_h.size, dtype=torch.float32, device=dev)
-        dist.broadcast(arena, 0)
-        eng = StepEngine(cfg, local)
-        eng.load_arena(arena, manifest)
-        del arena
-    else:
-        eng = StepEngine(cfg, local)
-        eng.load_weights(w)
-    loop = Loop(eng)
-    del w
-
-    # ---- synthetic initial conditions: base state + per-member Philox perturbation (K11) ----
-    base = torch.from_numpy(synthetic_state(CHANNELS, cfg.nlat, cfg.nlon, 0))
-    x = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
-    sigma = torch.from_numpy(channel_stats(CHANNELS)[1]).to(dev)
-    perturb_ic(x, sigma, 0.05, seed=0, member0=rank * M)
-    y = torch.empty_like(x)
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up + family breakdown (all families timed, outside the timed region) ----
-    for _ in range(max(args.warmup - 1, 0)):
+    def max(self, *vals):
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def min(self, *vals):
+        return [-v for v in self.max(*[-v for v in vals])]
+
+
+def build_engine(model: str, d: Dist):
+    """Weights built on rank 0, ONE NCCL broadcast of the fp32 arena (the only collective of the job), repacked per device."""
+    import numpy as np
+    import torch
+    from skyrim_b200.engine import StepEngine, pack_arena
+    if model == "sfno":
+        from skyrim_b200.config import FCNV2_CHANNELS as CH, sfno_full
+        from skyrim_b200.timeloop import SFNOTimeLoop as Loop
+        from skyrim_b200.weights import make_sfno_weights, sfno_param_shapes, sfno_table_shapes, sfno_tables
+        cfg = sfno_full()
+        w = None
+        if d.rank == 0:
+            w = make_sfno_weights(cfg, 0); w.update(sfno_tables(cfg))
+        shapes = None
+        if d.world > 1:
+            shapes = sfno_param_shapes(cfg)
+            shapes.update(sfno_table_shapes(cfg))
+    else:
+        from skyrim_b200.config import PANGU_CHANNELS as CH, pangu_full
+        from skyrim_b200.timeloop import PanguTimeLoop as Loop
+        from skyrim_b200.weights import make_pangu_weights, pangu_param_shapes
+        cfg = pangu_full()
+        w = make_pangu_weights(cfg, 0) if d.rank == 0 else None
+        shapes = pangu_param_shapes(cfg) if d.world > 1 else None
+    eng = StepEngine(cfg, d.local)
+    if d.world > 1:
+        import torch.distributed as dist
+        if d.rank == 0:
+            arena_h, manifest = pack_arena(w)
+            arena = torch.from_numpy(arena_h).to(d.dev)
+        else:
+            arena_h, manifest = pack_arena({k: np.zeros(s, np.float32) for k, s in shapes.items()})
+            arena = torch.empty(arena_h.size, dtype=torch.float32, device=d.dev)
+        del arena_h
+        dist.broadcast(arena, 0)
+        eng.load_arena(arena, manifest)
+        del arena
+    else:
+        eng.load_weights(w)
+    return cfg, CH, eng, Loop(eng)
+
+
+def family_roofline(model, cfg, M, fam_ms, peaks):
+    """Per kernel family: algorithmic FLOPs and mandatory HBM bytes per step (skyrim_b200/roofline.py) over
+    the family's measured device time per step -> achieved TFLOP/s, GB/s and the fraction of the bounding roofline."""
+    from skyrim_b200 import roofline as R
+    fl = R.sfno_flops(cfg) if model == "sfno" else R.pangu_flops(cfg)
+    by = R.sfno_bytes(cfg) if model == "sfno" else R.pangu_bytes(cfg)
+    out = {}
+    for k, ms in fam_ms.items():
+        f, b = M * fl.get(k, 0.0), M * by.get(k, 0.0)
+        if ms <= 0 or (f == 0 and b == 0):
+            continue
+        tf, gb = f / (ms * 1e-3) / 1e12, b / (ms * 1e-3) / 1e9
+        ft, fh = tf / peaks["tensor_sustained"], gb / peaks["hbm"]
+        bound = "tensor" if f / (peaks["tensor_sustained"] * 1e12) >= b / (peaks["hbm"] * 1e9) else "hbm"
+        out[k] = {"ms": round(ms, 4), "bound": bound, "tflops": round(tf, 1), "gbs": round(gb, 1),
+                  "frac": round(ft if bound == "tensor" else fh, 4), "frac_tensor": round(ft, 4), "frac_hbm": round(fh, 4)}
+    return out, fl, by
+
+
+def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool = True):
+    import torch
+    from skyrim_b200.engine import launch_count, perturb_ic
+    from skyrim_b200.verify import compare_fullsize, load_fixture, summarise
+    from skyrim_b200.weights import channel_stats, synthetic_state
+    cfg, CH, eng, loop = build_engine(model, d)
+    dev = d.dev
+    # ---- synthetic initial conditions: global member 0 is the unperturbed control (the fixture's IC), the others carry
+    # the Philox perturbation keyed by their global member id (K11) ----
+    base = torch.from_numpy(synthetic_state(CH, cfg.nlat, cfg.nlon, 0))
+    x0 = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
+    sigma = torch.from_numpy(channel_stats(CH)[1]).to(dev)
+    first = 1 if d.rank == 0 else 0
+    if M - first > 0:
+        perturb_ic(x0[first:], sigma, 0.05, seed=0, member0=d.rank * M + first)
+    x = x0.clone()
+    y, z = torch.empty_like(x), torch.empty_like(x)
+
+    # ---- warm-up on a copy + family breakdown (all families timed, outside the timed region) ----
+    for _ in range(max(warmup - 1, 0)):
         eng.step(x, y); x, y = y, x
     eng.profile_begin()
     eng.step(x, y); x, y = y, x
     fam = eng.profile_end()
+    fam_ms = {k: v[0] for k, v in fam.items()}
     dominant = max(fam, key=lambda k: fam[k][0])
+    x.copy_(x0)
 
-    # ---- timed region: K device-resident chained steps ----
-    sampler = ClockSampler(local)
+    # ---- timed region: K device-resident chained steps from the seeded IC; the first step's output stays in `z` ----
+    sampler = ClockSampler(d.local)
     launches0 = launch_count()
-    barrier()
+    d.barrier()
     sampler.start()
     eng.profile_begin([dominant])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        eng.step(x, y); x, y = y, x
+    eng.step(x, z)
+    src, dst = z, y
+    for _ in range(steps - 1):
+        eng.step(src, dst)
+        src, dst = dst, (x if dst is y else y)
     e1.record()
-    barrier()
+    d.barrier()
     clocks = sampler.stop()
     dom = eng.profile_end()[dominant]
     ms_total = e0.elapsed_time(e1)
     launches = launch_count() - launches0
-    finite = bool(torch.isfinite(x).all())
+    finite = bool(torch.isfinite(src).all())
+
+    # ---- verification of the timed run's first output against the full-size oracle fixture (rank 0, member 0) ----
+    verify = None
+    if d.rank == 0:
+        s = summarise(compare_fullsize(z[0], load_fixture(model)))
+        ok = bool(s["finite"] and finite and s["rel"] < VERIFY_TOL and s["norm"] < VERIFY_TOL and s["block"] < VERIFY_TOL_SIGMA)
+        verify = {"ok": ok, "against": f"tests/golden/{model}_721x1440_seed0.npz (one real oracle step)",
+                  "max_rel_err_per_channel": s["rel"], "max_rms_err_sigma": s["nrm"], "max_block_mean_err_sigma": s["block"],
+                  "max_norm_err": s["norm"], "tolerance": VERIFY_TOL, "rollout_finite": finite}
 
     # ---- end to end through the TimeLoop call: host (pinned) in, host (pinned) out, every step ----
-    xh = torch.empty((M,) + tuple(base.shape), dtype=torch.float32).pin_memory()
-    xh.copy_(x.cpu())
-    e2e_steps = max(3, min(args.steps, 10))
-    out_h = loop.step_host(xh)  # warm-up (allocates the pinned result buffer)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out_h = loop.step_host(out_h)  # H2D + step + D2H, synchronous result on the host
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
+    e2e_ms = None
+    if e2e:
+        xh = torch.empty((M,) + tuple(base.shape), dtype=torch.float32).pin_memory()
+        xh.copy_(x0.cpu())
+        e2e_steps = max(3, min(steps, 10))
+        out_h = loop.step_host(xh)  # warm-up (allocates the pinned result buffers)
+        d.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out_h = loop.step_host(out_h)  # H2D + step + D2H, synchronous result on the host
+        d.barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1000.0 / e2e_steps
+        del xh, out_h
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
-    ms_step = ms_total / args.steps
-    value = world * M * 1000.0 / ms_step
-
-    cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not sfno:
-        cb = cpu_reference(1, 0, 91)
-
-    if rank == 0:
-        peaks = _peaks()
-        fl = sfno_flops(cfg) if sfno else pangu_flops(cfg)
-        fam_flops = M * fl.get(dominant, 0.0)
-        n_l = dom[1] / args.steps
-        avg_ms = dom[0] / max(dom[1], 1)
-        achieved = fam_flops / max(n_l, 1) / (avg_ms * 1e-3) / 1e12 if fam_flops else None
+    ms_total, e2e_max = d.max(ms_total, e2e_ms or 0.0)
+    ms_step = ms_total / steps
+    rec = {"model": model, "members_per_gpu": M, "members_total": d.world * M, "steps": steps, "ms_per_step": ms_step,
+           "value": d.world * M * 1000.0 / ms_step, "unit": UNIT, "gpu_launches": int(launches), "clocks": clocks,
+           "verify": verify, "dominant": dominant, "dominant_launches_per_step": dom[1] / steps,
+           "dominant_avg_launch_ms": dom[0] / max(dom[1], 1)}
+    if e2e:
         sbytes = cfg.n_channels * cfg.nlat * cfg.nlon * 4 * M
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f16 hi+lo split operands (3-term) / f32 accumulate (tcgen05 kind::f16), f32 state" if sfno else
-                      "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, LN, softmax"),
-            "data": "synthetic",
-            "config": {"workload": ("FourCastNet-v2 SFNO rollout (chained 6-h steps), 73-channel synthetic (73,721,1440) IC, "
-                                    "state resident in HBM" if sfno else
-                                    "Pangu 7-day rollout (chained 6-h steps), synthetic (69,721,1440) IC, state "
-                                    "resident in HBM"), "members_per_gpu": M, "members_total": world * M,
-                       "l2": "inputs larger than L2 (state 0.3 GB + >2 GB activations streamed per step)",
-                       "weights": "synthetic seed 0", "finite": finite},
-            "e2e": {"value": world * M * 1000.0 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes,
-                    "path": "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dominant, "achieved": achieved,
-                         "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tensor_sustained"]) if achieved else None, "traffic": _traffic(dominant),
-                         "peak_source": peaks["source"] + " bf16 cuBLAS, sustained (kernel timed inside a long step)",
-                         "launches_per_step": n_l, "avg_launch_ms": avg_ms,
-                         "step_tflops": M * fl["total"] / (ms_step * 1e-3) / 1e12},
-            "families_ms_per_step": {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
-            "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        rec["e2e"] = {"value": d.world * M * 1000.0 / e2e_max, "unit": UNIT, "ms_per_step": e2e_max,
+                      "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes,
+                      "path": "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host"}
+    if d.rank == 0:
+        peaks = _peaks()
+        fams, fl, by = family_roofline(model, cfg, M, fam_ms, peaks)
+        rec["families"] = fams
+        rec["families_ms_per_step"] = {k: round(v, 3) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])}
+        rec["step_tflops"] = M * fl["total"] / (ms_step * 1e-3) / 1e12
+        rec["step_frac_tensor"] = rec["step_tflops"] / peaks["tensor_sustained"]
+        rec["_dominant_flops"] = M * fl.get(dominant, 0.0)
+        rec["_dominant_bytes"] = M * by.get(dominant, 0.0)
+    eng.close()
+    del eng, loop, x, y, z, x0
+    torch.cuda.empty_cache()
+    return rec
 
 
 def _traffic(family):
-    """DRAM bytes per launch of the dominant kernel family from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json, provenance inside); None when no capture covers the family."""
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f).get(family, {}).get("bytes_per_launch")
-    except (OSError, ValueError):
-        return None
+    """DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture of this round's kernels
+    (profiles/r2_traffic.json, provenance and kernel names inside); None when no capture covers the family."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(p) as f:
+                e = json.load(f).get(family)
+            if e:
+                return e.get("bytes_per_launch"), f"profiles/{name}"
+        except (OSError, ValueError):
+            pass
+    return None, None
+
+
+def run_ours(args):
+    import torch
+    d = Dist(args)
+    M = args.members_per_gpu
+    head = bench_model(args.model, M, args.steps, args.warmup, d)
+    subs = {}
+    if not args.only_headline:
+        k = max(3, min(args.steps, 8))
+        if args.model != "sfno":
+            subs["sfno"] = bench_model("sfno", 1, k, 3, d, e2e=(d.world == 1))
+        if args.model == "pangu" and M != 4:
+            subs["ensemble_m4"] = bench_model("pangu", 4, k, 3, d, e2e=False)
+    cb = None
+    if d.rank == 0 and d.world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference(1)
+
+    if d.rank == 0:
+        peaks = _peaks()
+        dom = head["dominant"]
+        fam = head["families"].get(dom, {})
+        tensor_bound = fam.get("bound", "tensor") == "tensor"
+        n_l, avg_ms = head["dominant_launches_per_step"], head["dominant_avg_launch_ms"]
+        work = head["_dominant_flops"] if tensor_bound else head["_dominant_bytes"]
+        achieved = work / max(n_l, 1) / (avg_ms * 1e-3) / (1e12 if tensor_bound else 1e9)
+        peak = peaks["tensor_sustained"] if tensor_bound else peaks["hbm"]
+        traffic, tsrc = _traffic(dom)
+        sfno = args.model == "sfno"
+        for r in [head] + list(subs.values()):
+            r.pop("_dominant_flops", None); r.pop("_dominant_bytes", None)
+        if "ensemble_m4" in subs:   # config 5: ratio of the 4-members-per-GPU job to ONE member on ONE GPU (target >= 7.5 at 8 GPUs)
+            subs["ensemble_m4"]["vs_one_member_one_gpu"] = subs["ensemble_m4"]["value"] / (head["value"] / (d.world * M))
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": d.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": ("f16 hi+lo split operands / f32 accumulate (tcgen05 kind::f16), f32 state" if sfno else
+                      "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, LN, softmax"),
+            "data": "synthetic",
+            "config": {"workload": ("FourCastNet-v2 SFNO rollout (chained 6-h steps), synthetic (73,721,1440) IC, state resident in HBM"
+                                    if sfno else
+                                    "Pangu 7-day rollout (chained 6-h steps), synthetic (69,721,1440) IC, state resident in HBM"),
+                       "members_per_gpu": M, "members_total": d.world * M,
+                       "l2": "inputs larger than L2 (state 0.3 GB + >2 GB activations streamed per step)",
+                       "weights": "synthetic seed 0", "verified_against_oracle_fixture": bool(head["verify"] and head["verify"]["ok"])},
+            "e2e": head.get("e2e"),
+            "gpu_launches": head["gpu_launches"],
+            "clocks": head["clocks"],
+            "roofline": {"bound": "tensor" if tensor_bound else "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": tsrc, "peak_source": peaks["source"] + (", bf16 cuBLAS sustained (kernel timed inside a long step)"
+                                                                                   if tensor_bound else ", device copy"),
+                         "launches_per_step": n_l, "avg_launch_ms": avg_ms, "step_tflops": head["step_tflops"],
+                         "step_frac_tensor": head["step_frac_tensor"]},
+            "families": head["families"],
+            "families_ms_per_step": head["families_ms_per_step"],
+            "verify": head["verify"],
+            "configs": subs,
+            "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+        }
+        print(json.dumps(line), flush=True)
+        bad = [m for m, r in [("headline", head)] + list(subs.items()) if r["verify"] and not r["verify"]["ok"]]
+        if bad:
+            print(f"bench.py: output verification against the oracle fixture FAILED for {bad}", file=sys.stderr)
+            if "headline" in bad and not args.allow_unverified:   # a fast, finite, wrong headline number is not a number
+                sys.exit(3)
+    if d.world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def main():
@@ -310,8 +455,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members-per-gpu", type=int, default=1)
     ap.add_argument("--model", default="pangu", choices=["pangu", "sfno"],
-                    help="pangu (default, the headline workload) or sfno (FourCastNet-v2 73-channel rollout)")
+                    help="headline workload: pangu (default) or sfno (FourCastNet-v2 73-channel rollout)")
+    ap.add_argument("--only-headline", action="store_true", help="skip the configs.sfno / configs.ensemble_m4 sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allow-unverified", action="store_true",
+                    help="print the line (verify.ok = false) instead of exiting 3 when the fixture comparison fails")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -37,8 +37,10 @@ class SFNORef:
             self.tabs[tag] = dict(fwd=torch.from_numpy(fwd).to(dtype), inv=torch.from_numpy(inv).to(dtype), nlon=nlon, nlat=nlat)
         self.cd = cd
 
-    def _q(self, t):
-        if self.emulate == "fp16":
+    def _q(self, t, tag="all"):
+        """operand rounding emulation: emulate = "fp16" rounds every GEMM operand to half; a set / tuple of tags
+        ("mlp", "dft", "leg", "spec") rounds only those contractions (precision-budget studies, tests/test_sfno_cpu.py)"""
+        if self.emulate == "fp16" or (isinstance(self.emulate, (set, frozenset, tuple, list)) and tag in self.emulate):
             if t.is_complex():
                 return torch.complex(t.real.half().to(self.dtype), t.imag.half().to(self.dtype))
             return t.half().to(self.dtype)
@@ -47,17 +49,17 @@ class SFNORef:
     # -- transforms (channel-major (C, nlat, nlon) <-> complex (C, lmax, mmax)) -----------------
     def sht(self, x, tag):
         t = self.tabs[tag]
-        f = 2.0 * np.pi * torch.fft.rfft(self._q(x), dim=-1, norm="forward")[..., : self.cfg.mmax]
-        f = self._q(f)
-        return torch.einsum("mlk,ckm->clm", self._q(t["fwd"]).to(self.cd), f)
+        f = 2.0 * np.pi * torch.fft.rfft(self._q(x, "dft"), dim=-1, norm="forward")[..., : self.cfg.mmax]
+        f = self._q(f, "leg")
+        return torch.einsum("mlk,ckm->clm", self._q(t["fwd"], "leg").to(self.cd), f)
 
     def isht(self, X, tag):
         t = self.tabs[tag]
-        f = torch.einsum("mkl,clm->ckm", self._q(t["inv"]).to(self.cd), self._q(X))
-        return torch.fft.irfft(self._q(f), n=t["nlon"], dim=-1, norm="forward")
+        f = torch.einsum("mkl,clm->ckm", self._q(t["inv"], "leg").to(self.cd), self._q(X, "leg"))
+        return torch.fft.irfft(self._q(f, "dft"), n=t["nlon"], dim=-1, norm="forward")
 
     def _conv1x1(self, x, w, b=None):  # x (C, H, W)
-        y = torch.einsum("oc,chw->ohw", self._q(w), self._q(x))
+        y = torch.einsum("oc,chw->ohw", self._q(w, "mlp"), self._q(x, "mlp"))
         return y if b is None else y + b[:, None, None]
 
     def _inorm(self, x, g, b):
@@ -72,7 +74,7 @@ class SFNORef:
         X = self.sht(xn, tin)
         residual = xn if tin == tout else self.isht(X, tout)
         wc = torch.complex(w[p + "spec.w"][..., 0], w[p + "spec.w"][..., 1])  # (l, out, in)
-        Xo = torch.einsum("loi,ilm->olm", self._q(wc), self._q(X))
+        Xo = torch.einsum("loi,ilm->olm", self._q(wc, "spec"), self._q(X, "spec"))
         y = self.isht(Xo, tout)
         y = y + self._conv1x1(residual, w[p + "inner.w"], w[p + "inner.b"])
         y = F.gelu(y)

@@ -19,6 +19,13 @@ class FourcastnetV2Model(GlobalModel):
         from ...engine import StepEngine
         from ...timeloop import SFNOTimeLoop
         from ...weights import make_sfno_weights, sfno_tables
+        import os
+        real = os.environ.get("SKYRIM_B200_WEIGHTS_FCNV2")
+        if self._weights is None and real:
+            # fcnv2_sm checkpoint directory (weights.tar + global_means.npy / global_stds.npy: what fcnv2_sm.load reads in
+            # the reference, fourcastnet_v2.py:36-37); hyper-parameters come from the tensor shapes
+            from ...importers import load_real_weights
+            self._cfg, self._weights = load_real_weights("sfno", real)
         eng = StepEngine(self._cfg, self._device)
         w = dict(self._weights if self._weights is not None else make_sfno_weights(self._cfg, self._seed))
         w.update(sfno_tables(self._cfg))

@@ -20,10 +20,17 @@ class PanguModel(GlobalModel):
         from ...engine import StepEngine
         from ...timeloop import PanguTimeLoop
         from ...weights import make_pangu_weights
+        import os
+        w = self._weights
+        real = os.environ.get("SKYRIM_B200_WEIGHTS")
+        if w is None and real:
+            # real checkpoint on disk (what pangu.load(registry.get_model("e2mip://pangu")) downloads in the reference,
+            # pangu.py:45-46): ONNX initialisers -> engine parameters, no onnx / onnxruntime needed (importers.py)
+            from ...importers import load_real_weights
+            _, w = load_real_weights("pangu", real)
         eng = StepEngine(self._cfg, self._device)
-        # no network: real checkpoints cannot be downloaded here, the engine runs on seeded
-        # synthetic weights unless a weight dict is supplied
-        eng.load_weights(self._weights if self._weights is not None else make_pangu_weights(self._cfg, self._seed))
+        # no network here: without SKYRIM_B200_WEIGHTS or a weight dict the engine runs on seeded synthetic weights
+        eng.load_weights(w if w is not None else make_pangu_weights(self._cfg, self._seed))
         return PanguTimeLoop(eng)
 
     @property

@@ -33,6 +33,34 @@ def pangu_flops(cfg: PanguConfig) -> dict:
     return f
 
 
+def pangu_bytes(cfg: PanguConfig) -> dict:
+    """Mandatory HBM bytes per 6-h step and kernel family for the data flow of DESIGN.md section 3 (fp32 residual stream x,
+    fp16 operand images xh; weights stay in L2 and are not counted).  Per token and feature:
+      qkv    read xh 2 B, write q|k|v window images 3 x 2 B (padded tokens included)
+      attn   read q|k|v 6 B, write the projection's operand image 2 B
+      proj   read operand image 2 B, residual x read 4 B + write 4 B, next operand image 2 B
+      mlp    read xh 2 B, x read + write 8 B, xh write 2 B (the 4C hidden activation never leaves the SM)"""
+    C = cfg.dim
+    HW = cfg.H * cfg.W
+    T1, T2 = cfg.Z * HW, cfg.Z * cfg.H2 * cfg.W2
+    nwin1 = (cfg.Z // 2) * (cfg.padded_h(cfg.H) // 6) * (cfg.W // 12)
+    nwin2 = (cfg.Z // 2) * (cfg.padded_h(cfg.H2) // 6) * (cfg.W2 // 12)
+    b = dict(qkv=0.0, attn=0.0, proj=0.0, mlp=0.0)
+    for li, depth in enumerate(cfg.depths):
+        c, T, rows = (C, T1, nwin1 * WIN_TOK) if li in (0, 3) else (2 * C, T2, nwin2 * WIN_TOK)
+        b["qkv"] += depth * (2.0 * T * c + 6.0 * rows * c)
+        b["attn"] += depth * (6.0 * rows * c + 2.0 * T * c)
+        b["proj"] += depth * 12.0 * T * c
+        b["mlp"] += depth * 12.0 * T * c
+    state = float(pangu_state_bytes(cfg))
+    b["embed"] = state + T1 * C * (4.0 + 2.0)                  # state in; x (fp32) + operand image out
+    b["recover"] = 2.0 * T1 * C * 2.0 + state                  # concat(skip, x) images in; state out
+    b["down"] = T1 * C * 4.0 + T2 * 4 * C * 2.0 * 2 + T2 * 2 * C * (4.0 + 2.0)   # x in, merged image out + in, x2 + image out
+    b["up"] = T2 * 2 * C * 2.0 + T1 * C * 2.0 * 2 + T1 * C * (4.0 + 2.0)       # image in, shuffled image out + in, x1 + image out
+    b["total"] = sum(b.values())
+    return b
+
+
 def pangu_state_bytes(cfg: PanguConfig) -> int:
     return cfg.n_channels * cfg.nlat * cfg.nlon * 4
 
@@ -57,3 +85,20 @@ def sfno_flops(cfg: SFNOConfig) -> dict:
     f["sfno_mlp"] = (L - 1) * mlp_int + mlp_big
     f["total"] = sum(f.values())
     return f
+
+
+def sfno_bytes(cfg: SFNOConfig) -> dict:
+    """Mandatory HBM bytes per step and family with fp32 activations between stages (E channels; pixels P1 at 721x1440,
+    P2 on the internal grid); spectral weights are streamed once per step and layer."""
+    E, Cin, L = cfg.embed, cfg.n_channels, cfg.layers
+    P1, P2 = cfg.nlat * cfg.nlon, cfg.h * cfg.w
+    lm = cfg.lmax * cfg.mmax
+    b = {}
+    b["sfno_enc"] = 4.0 * P1 * (Cin + E) + 4.0 * P1 * E          # state in, x out, positional embedding in
+    b["sfno_dec"] = 4.0 * P1 * (E + Cin + Cin)
+    b["sfno_sht"] = 4.0 * E * (P1 + (L - 1) * P2) + 8.0 * L * E * lm
+    b["sfno_isht"] = 8.0 * (L + 2) * E * lm + 4.0 * E * (2 * P1 + L * P2)
+    b["sfno_spec"] = L * (8.0 * cfg.lmax * E * E + 16.0 * E * lm)
+    b["sfno_mlp"] = 4.0 * E * 4 * ((L - 1) * P2 + P1)
+    b["total"] = sum(b.values())
+    return b

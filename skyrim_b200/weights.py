@@ -256,6 +256,19 @@ def make_sfno_weights(cfg: SFNOConfig, seed: int = 0) -> "OrderedDict[str, np.nd
     return OrderedDict((k, out[k]) for k in sfno_param_shapes(cfg))
 
 
+def sfno_table_shapes(cfg: SFNOConfig) -> "OrderedDict[str, tuple]":
+    """Shapes (and order) of sfno_tables() without computing them: what a non-root rank needs for the arena manifest."""
+    t = OrderedDict()
+    t["sht.fwd_big"] = (cfg.mmax, cfg.lmax, cfg.nlat)
+    t["sht.inv_big"] = (cfg.mmax, cfg.nlat, cfg.lmax)
+    t["sht.fwd_int"] = (cfg.mmax, cfg.lmax, cfg.h)
+    t["sht.inv_int"] = (cfg.mmax, cfg.h, cfg.lmax)
+    for tag, n in (("big", cfg.nlon), ("int", cfg.w)):
+        t[f"dft.fwd_{tag}"] = (2 * cfg.mmax, n)
+        t[f"dft.inv_{tag}"] = (n, 2 * cfg.mmax)
+    return t
+
+
 def sfno_tables(cfg: SFNOConfig) -> "OrderedDict[str, np.ndarray]":
     """SHT / DFT tables the engine consumes as extra arena entries (fp32)."""
     from .sht import dft_matrices, sht_tables

@@ -127,13 +127,61 @@ def test_skyrim_facade_validates_names():
         Skyrim("not_a_model")
 
 
-def test_bench_traffic_lookup_reads_the_committed_ncu_numbers():
-    """bench.py's roofline.traffic comes from profiles/r1_traffic.json (one `ncu --set full` capture per round)."""
+def test_predict_one_step_returns_ic_and_one_prediction():
+    """A4 (reference base.py:80-92): predict_one_step == run_basic_inference(n=1): IC slice + one 6-h prediction."""
+    gm = BoringGlobalModel(ic_source="synthetic")
+    t0 = datetime.datetime(2024, 5, 7)
+    da = gm.predict_one_step(t0)
+    assert da.dims == ("time", "channel", "lat", "lon") and da.shape == (2, 4, 19, 36)
+    np.testing.assert_allclose(da.values[1], da.values[0] + 1.0)
+    f = gm.forecast(t0, n_steps=2)
+    np.testing.assert_array_equal(f.values[:2], da.values)            # forecast's first two slices are the same step
+    # stepping from a supplied state (the path rollout() uses for every step after the first)
+    da2 = gm.predict_one_step(t0 + datetime.timedelta(hours=6), initial_condition=da.isel(time=[1]))
+    np.testing.assert_allclose(da2.values[1], da.values[0] + 2.0, rtol=0, atol=1e-5)
+
+
+def test_forecast_cli_mirrors_the_reference_options(tmp_path, monkeypatch):
+    """reference skyrim/forecast.py:59-151: option names / short flags / defaults; run_forecast returns the saved paths."""
+    from click.testing import CliRunner
+    from skyrim_b200 import forecast as F
+    from skyrim_b200.core import models as M
+    opts = {o.name: o for o in F.main.params}
+    for name, short in [("model_name", "-m"), ("date", "-d"), ("time", "-t"), ("lead_time", "-l"), ("list_models", "-lm"),
+                        ("initial_conditions", "-ic"), ("output_dir", "-o"), ("filter_vars", "-f"), ("modal", "-mo")]:
+        assert name in opts and short in opts[name].opts, name
+    assert opts["lead_time"].default == 6 and opts["time"].default == "0000" and opts["model_name"].default == "pangu"
+    r = CliRunner().invoke(F.main, ["-lm"])
+    assert r.exit_code == 0 and "pangu" in r.output and "fourcastnet_v2" in r.output
+    assert CliRunner().invoke(F.main, ["-mo"]).exit_code != 0
+
+    class FakePangu(BoringGlobalModel):
+        def __init__(self, ic_source="synthetic", **kw):
+            super().__init__(ic_source=ic_source)
+    monkeypatch.setitem(M.MODELS, "pangu", FakePangu)
+    r = CliRunner().invoke(F.main, ["-m", "pangu", "-d", "20240507", "-t", "0600", "-l", "13", "-o", str(tmp_path), "-f", "t2m,msl"])
+    assert r.exit_code == 0, r.output
+    paths = [ln for ln in r.output.splitlines() if ln.endswith(".nc") or ln.endswith(".zarr")]
+    assert len(paths) == 2                                           # lead 13 h -> floored to 12 h -> two 6-h steps
+    da = xr.open_dataarray(paths[0])
+    assert list(da.coords["channel"]) == ["t2m", "msl"]
+
+
+def test_bench_traffic_lookup_and_roofline_tables():
+    """bench.py's roofline.traffic comes from a committed `ncu --set full` capture (profiles/r*_traffic.json); the per-family
+    roofline uses skyrim_b200/roofline.py's FLOP and byte tables."""
     import importlib.util, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    t = mod._traffic("mlp")
-    assert isinstance(t, int) and 3e8 < t < 2e9   # bytes per launch of the fused MLP (algorithmic: 0.75e9)
-    assert mod._traffic("no-such-family") is None
+    t, src = mod._traffic("mlp")
+    assert isinstance(t, int) and 3e8 < t < 2e9 and src.startswith("profiles/")   # bytes per launch of the fused MLP
+    assert mod._traffic("no-such-family") == (None, None)
+    from skyrim_b200.config import pangu_full, sfno_full
+    fams, fl, by = mod.family_roofline("pangu", pangu_full(), 1, {"mlp": 5.0, "attn": 2.0, "embed": 0.3},
+                                       dict(hbm=6572.0, tensor_sustained=1431.0))
+    assert fams["mlp"]["bound"] == "tensor" and fams["attn"]["bound"] == "hbm" and 0.5 < fams["attn"]["frac"] < 0.8
+    assert abs(fl["total"] - 8.26e12) < 0.2e12 and 40e9 < by["total"] < 50e9
+    fams, fl, by = mod.family_roofline("sfno", sfno_full(), 1, {"sfno_mlp": 5.0}, dict(hbm=6572.0, tensor_sustained=1431.0))
+    assert "sfno_mlp" in fams and 2e12 < fl["total"] < 6e12
