@@ -189,7 +189,10 @@ struct EpiF32Batched {
       patch_put_s(e.patch_s, e.lane, v);
       __syncwarp();
       const int col = e.n0 + c + c4 * 4;
-      if (col < n_valid) {
+      // BN need not be a multiple of 32 (16, 80, 240): the 32-column TMEM read then runs past the tile; those columns
+      // belong to the NEXT n-tile (another CTA's work) and must not be stored from here (round-1 bug: they were, and
+      // raced with the owner's store whenever N had more than one such tile, e.g. nlon = 1440 or lmax = 240)
+      if (col < n_valid && c + c4 * 4 < BN) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll

@@ -57,12 +57,22 @@ class EnsembleRunner:
         return self.x
 
     def mean_and_spread(self, world: int = 1):
-        """ensemble mean / standard deviation over ALL members (one all-reduce, outside the loop)"""
-        import torch
-        import torch.distributed as dist
-        s, ss = self.x.sum(0), (self.x * self.x).sum(0)
-        if world > 1:
-            dist.all_reduce(s); dist.all_reduce(ss)
-        n = world * self.M
-        mean = s / n
-        return mean, (ss / n - mean * mean).clamp_min(0).sqrt()
+        """ensemble mean / standard deviation over ALL members (two all-reduces, outside the step loop)"""
+        return mean_and_spread(self.x, world)
+
+
+def mean_and_spread(x, world: int = 1):
+    """x: this rank's members (M, C, H, W).  Two-pass: the mean is reduced first, then the sum of squared DEVIATIONS —
+    E[x^2] - mean^2 in fp32 cancels catastrophically on de-normalised fields (z ~ 5e4, t ~ 280 with a spread of a few
+    units), and clamping hid the negative variances it produced."""
+    import torch
+    import torch.distributed as dist
+    n = world * x.shape[0]
+    s = x.sum(0, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(s)
+    mean = (s / n).to(x.dtype)
+    ss = ((x - mean) ** 2).sum(0, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ss)
+    return mean, (ss / n).sqrt().to(x.dtype)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from skyrim_b200.config import pangu_small
-from skyrim_b200.ensemble import broadcast_arena, member_range
+from skyrim_b200.ensemble import broadcast_arena, mean_and_spread, member_range
 from skyrim_b200.weights import make_pangu_weights, pangu_param_shapes
 
 
@@ -23,6 +23,12 @@ def _worker(rank, world, port, q):
     ok = True
     for d, (k, a) in zip(manifest, ref.items()):
         ok &= d.name.decode() == k and np.array_equal(arena[d.offset:d.offset + d.count].numpy(), a.reshape(-1))
+    # ensemble statistics across ranks: 2 members per rank of a field with a large mean and a small spread
+    g = torch.Generator().manual_seed(7)
+    allm = 5.0e4 + 0.5 * torch.randn(4, 2, 8, 16, generator=g)
+    mean, spread = mean_and_spread(allm[2 * rank:2 * rank + 2].clone(), world)
+    ok &= bool(torch.allclose(mean, allm.mean(0), rtol=0, atol=1e-2))
+    ok &= bool(torch.allclose(spread, allm.double().std(0, unbiased=False).float(), rtol=1e-3, atol=1e-4))
     q.put((rank, bool(ok), list(member_range(rank, 4)), float(arena.sum())))
     dist.destroy_process_group()
 
