@@ -63,58 +63,67 @@ typedef struct {
 
 typedef struct sky_model sky_model_t;
 
-int sky_abi_version(void);
-const char* sky_last_error(void);
+/* Everything but these entry points is built with hidden visibility: the product and the development build of the
+ * library can then live in one process without their template statics / inline functions being merged by the
+ * dynamic linker (round 2: a shared `configured` flag made the second library skip its shared-memory opt-in). */
+#if defined(__GNUC__)
+#define SKY_API __attribute__((visibility("default")))
+#else
+#define SKY_API
+#endif
+
+SKY_API int sky_abi_version(void);
+SKY_API const char* sky_last_error(void);
 
 /* model_kind: SKY_MODEL_*; cfg points at the matching sky_*_config_t. */
-int sky_model_create(sky_model_t** out, int model_kind, const void* cfg, size_t cfg_bytes, int device);
+SKY_API int sky_model_create(sky_model_t** out, int model_kind, const void* cfg, size_t cfg_bytes, int device);
 
 /* Load (copy + repack for the tensor cores) the fp32 weight arena.  `arena` is a host
  * pointer (arena_on_device = 0) or a device pointer on the model's device (= 1, e.g. the
  * buffer that received the one-time NCCL broadcast).  The caller keeps ownership.
  * Replaces ONNX initialiser loading / torch.load in the reference back-ends. */
-int sky_model_load_weights(sky_model_t* m, const float* arena, uint64_t n_floats,
+SKY_API int sky_model_load_weights(sky_model_t* m, const float* arena, uint64_t n_floats,
                            const sky_param_desc_t* manifest, int32_t n_params, int32_t arena_on_device,
                            void* stream);
 
 /* scratch bytes one step needs for `batch` members */
-size_t sky_model_workspace_bytes(const sky_model_t* m, int32_t batch);
+SKY_API size_t sky_model_workspace_bytes(const sky_model_t* m, int32_t batch);
 
 /* One 6-h step for `batch` independent members: x_in, x_out are device fp32
  * (batch, C, nlat, nlon), may not alias.  Asynchronous and stream-ordered; no host sync.
  * Replaces one `next()` of the TimeLoop generator (utils.py:34). */
-int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batch, void* workspace,
+SKY_API int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batch, void* workspace,
                    size_t workspace_bytes, void* stream);
 
 /* Intermediate tensor taps for kernel-level parity tests: after a step, copy the named
  * internal buffer ("embed"/"tokens1"/"tokens2"...) of the LAST step into dst (device fp32). */
-int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* workspace,
+SKY_API int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* workspace,
                          int32_t batch, void* stream);
 
 /* Debug switches of a handle (tests only; never read from the environment): "stop_after" = n makes step() return after
  * stage n (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3; 99 = run the whole step) so that
  * sky_model_debug_copy can read the intermediate token buffers. */
-int sky_model_debug_set(sky_model_t* m, const char* key, int64_t value);
+SKY_API int sky_model_debug_set(sky_model_t* m, const char* key, int64_t value);
 
 /* x[m, c, :, :] += amp * sigma[c] * N(0,1), Philox4x32-10 keyed by (seed, member0 + m):
  * perturbed-IC ensemble members (new functionality; the reference's only perturbation
  * helper is the single-point edit at models/utils.py:70-92). */
-int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int32_t member0,
+SKY_API int sky_perturb_ic(float* x, const float* sigma_c, float amp, uint64_t seed, int32_t member0,
                    int32_t members, int32_t channels, int64_t plane, void* stream);
 
 /* Per-kernel-family device timing (CUDA events recorded on the launching stream around the
  * launches whose family bit is set in tag_mask).  profile_end synchronises on the recorded
  * events and returns the summed milliseconds and launch counts per family.  Used by bench.py
  * for the live roofline figure; off by default (no events are recorded). */
-int sky_model_profile_begin(sky_model_t* m, uint64_t tag_mask);
-int sky_model_profile_end(sky_model_t* m, double* ms_per_tag, uint64_t* launches_per_tag, int32_t n_tags);
-int sky_profile_tag_count(void);
-const char* sky_profile_tag_name(int32_t tag);
+SKY_API int sky_model_profile_begin(sky_model_t* m, uint64_t tag_mask);
+SKY_API int sky_model_profile_end(sky_model_t* m, double* ms_per_tag, uint64_t* launches_per_tag, int32_t n_tags);
+SKY_API int sky_profile_tag_count(void);
+SKY_API const char* sky_profile_tag_name(int32_t tag);
 
 /* how many kernels this library has launched since load (bench.py's gpu_launches) */
-uint64_t sky_launch_count(void);
+SKY_API uint64_t sky_launch_count(void);
 
-int sky_model_destroy(sky_model_t* m);
+SKY_API int sky_model_destroy(sky_model_t* m);
 
 #ifdef __cplusplus
 }

@@ -212,4 +212,62 @@ struct EpiF32Batched {
   }
 };
 
+// acc (+ bias, optional GELU) -> hi / lo fp16 operand images of the NEXT GEMM (K = this GEMM's N): the 3-term split is
+// produced where the value is produced, instead of an fp32 round trip through HBM and a separate pack pass.
+// Same re-tiling as Epi2F16<.., kImage = true>: lane -> (row = it*8 + lane/4, 8-column chunk = lane%4), 16-byte stores.
+template <bool kGelu>
+struct EpiSplitImg {
+  static constexpr bool kNeedsBias = false;
+  uint8_t* hi; uint8_t* lo; int nkb;   // k-blocks per row tile of the destination images
+  const float* bias; int n_valid;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtxB& x) const {
+    const int rsub = x.lane >> 2, ch = x.lane & 3;
+    const uint32_t r0 = (uint32_t)(x.row0 & 127);
+    for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
+      const int col = x.n0 + c + ch * 8;                       // first of this lane's 8 columns
+      const bool cols_ok = c + ch * 8 < BN && col < n_valid;   // BN need not be a multiple of 32
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (!kGelu && cols_ok) { b0 = __ldg(reinterpret_cast<const float4*>(bias + col)); b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4)); }
+      {
+        float v[32];
+        acc.load32(c, v);
+        if (kGelu) {   // activation in the row domain: 32 independent chains per thread
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int cj = x.n0 + c + 4 * j;
+            const float4 b = cj < n_valid ? __ldg(reinterpret_cast<const float4*>(bias + cj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gelu_erf_x2(v[4 * j], v[4 * j + 1], b.x, b.y);
+            gelu_erf_x2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
+          }
+        }
+        patch_put_v(x.patch_s, x.lane, v);
+      }
+      __syncwarp();
+      const size_t tbase = ((size_t)(x.row0 >> 7) * nkb + (size_t)((x.n0 + c) >> 6)) * (size_t)G2_A_BYTES + (size_t)r0 * 128;
+      const uint32_t cb = (((uint32_t)(x.n0 + c) & 63u) >> 3) + (uint32_t)ch;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + rsub;
+        float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+        float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+        if (!kGelu) {
+          t0.x += b0.x; t0.y += b0.y; t0.z += b0.z; t0.w += b0.w;
+          t1.x += b1.x; t1.y += b1.y; t1.z += b1.z; t1.w += b1.w;
+        }
+        const float f[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        __half h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { h[e] = __float2half_rn(f[e]); l[e] = __float2half_rn(f[e] - __half2float(h[e])); }
+        if (cols_ok && x.row0 + rr < x.M) {
+          const size_t off = tbase + (size_t)rr * 128 + ((cb ^ (uint32_t)((r0 + rr) & 7)) << 4);
+          *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
 }  // namespace sky

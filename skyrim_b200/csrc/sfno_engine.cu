@@ -457,6 +457,17 @@ struct SfnoEngine : Engine {
     return gemm_epi(tag, A, nkb, a_bstride_bytes, mt, e, w, M, st);
   }
 
+  // D (+bias, optional GELU) written directly as the hi / lo operand images of the next GEMM (no fp32 round trip, no pack)
+  int gemm_to_img(int tag, const Img2& A, int K, long long rows, Img2& out, int Nout, const float* bias, bool gelu,
+                  const W3& w, cudaStream_t st) {
+    const int nkb = pad_to(K, 64) / 64, mt = pad_to((int)rows, 128) / 128;
+    const size_t need = (size_t)mt * (pad_to(Nout, 64) / 64) * G2_A_BYTES;
+    if (need > out.bytes || Nout % 64) { set_error("internal: split-image epilogue target (%zu > %zu, N=%d)", need, out.bytes, Nout); return SKY_ERR_STATE; }
+    if (gelu) { EpiSplitImg<true> e{out.hi, out.lo, Nout / 64, bias, w.N}; return gemm_epi(tag, A, nkb, 0, mt, e, w, rows, st); }
+    EpiSplitImg<false> e{out.hi, out.lo, Nout / 64, bias, w.N};
+    return gemm_epi(tag, A, nkb, 0, mt, e, w, rows, st);
+  }
+
   int norm_stats(const float* x, long long P, int act, const float* g, const float* b, cudaStream_t st) {
     prof_begin(KT_SFNO_MISC, st);
     SKY_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * E * sizeof(double), st));
@@ -535,11 +546,11 @@ struct SfnoEngine : Engine {
     // norm1(GELU(y)) -> MLP
     if ((rc = norm_stats(F1, Po, 1, b.n1g, b.n1b, st))) return rc;
     if ((rc = pack(KT_SFNO_MLP, F1, I_b, 1, 1, (int)Po, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 1, 0, 1, 2, 3, st))) return rc;
-    if ((rc = gemm(KT_SFNO_MLP, I_b, E, 0, Po, F1, Hd, 0, b.fc1_b, false, b.fc1, Po, st))) return rc;
-    if ((rc = pack(KT_SFNO_MLP, F1, I_b, 1, 1, (int)Po, Hd, 0, 0, Hd, 2, 1, 0, nullptr, nullptr, 1, 0, 1, 2, 3, st))) return rc;
+    // GELU(fc1) goes straight into the operand images of fc2 (I_a: the residual image it held was consumed by the inner skip)
+    if ((rc = gemm_to_img(KT_SFNO_MLP, I_b, E, Po, I_a, Hd, b.fc1_b, true, b.fc1, st))) return rc;
     // x_out = residual + fc2(...)   (accumulate onto a copy of the residual)
     SKY_CUDA_OK(cudaMemcpyAsync(xout, Rpm, (size_t)Po * E * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = gemm(KT_SFNO_MLP, I_b, Hd, 0, Po, xout, E, 0, b.fc2_b, true, b.fc2, Po, st))) return rc;
+    if ((rc = gemm(KT_SFNO_MLP, I_a, Hd, 0, Po, xout, E, 0, b.fc2_b, true, b.fc2, Po, st))) return rc;
     float* tmp = xin; xin = xout; xout = tmp;
     return 0;
   }
@@ -548,8 +559,7 @@ struct SfnoEngine : Engine {
     int rc;
     // encoder
     if ((rc = pack(KT_SFNO_ENC, x_in, I_in, 1, 1, (int)P1, Cin, 0, 0, 1, 2LL * P1, P1, 2, in_sc, in_sh, 0, 1, 0, 2, 3, st))) return rc;
-    if ((rc = gemm(KT_SFNO_ENC, I_in, Cin, 0, P1, F1, E, 0, enc1_b, false, enc1, P1, st))) return rc;
-    if ((rc = pack(KT_SFNO_ENC, F1, I_a, 1, 1, (int)P1, E, 0, 0, E, 2, 1, 0, nullptr, nullptr, 1, 0, 1, 2, 3, st))) return rc;
+    if ((rc = gemm_to_img(KT_SFNO_ENC, I_in, Cin, P1, I_a, E, enc1_b, true, enc1, st))) return rc;   // GELU(fc1) -> split images
     SKY_CUDA_OK(cudaMemcpyAsync(X, pos_pm, (size_t)P1 * E * 4, cudaMemcpyDeviceToDevice, st));
     if ((rc = gemm(KT_SFNO_ENC, I_a, E, 0, P1, X, E, 0, enc2_b, true, enc2, P1, st))) return rc;
     float *a = X, *b = Xn;
@@ -563,10 +573,9 @@ struct SfnoEngine : Engine {
       const int kx = E / 64, ki = pad_to(Cin, 64) / 64;
       const uint8_t* segs[6] = {I_a.hi, I_in.hi, I_a.lo, I_in.lo, I_a.hi, I_in.hi};
       for (int s = 0; s < 6; ++s) { op.seg[s] = segs[s]; op.nkb[s] = (s & 1) ? ki : kx; op.batch_stride[s] = 0; }
-      EpiF32Batched<false> e{F1, E, 0, dec1_b, dec1.N};
+      EpiSplitImg<true> e{I_b.hi, I_b.lo, E / 64, dec1_b, dec1.N};   // GELU(fc1) -> operand images of fc2
       if ((rc = gemm_op(KT_SFNO_DEC, op, e, dec1, P1, st))) return rc;
     }
-    if ((rc = pack(KT_SFNO_DEC, F1, I_b, 1, 1, (int)P1, E, 0, 0, E, 2, 1, 0, nullptr, nullptr, 1, 0, 1, 2, 3, st))) return rc;
     {
       EpiStateOut e{x_out, P1, Cin, dec2_b, mean, stdv};
       if ((rc = gemm_epi(KT_SFNO_DEC, I_b, E / 64, 0, 0, e, dec2, P1, st))) return rc;

@@ -68,7 +68,7 @@ class StepEngine:
             raise TypeError(cfg)
         self.n_channels = cfg.n_channels
         h = C.c_void_p()
-        _ffi.check(L.sky_model_create(C.byref(h), kind, C.byref(cc), C.sizeof(cc), device), "sky_model_create")
+        _ffi.check(L.sky_model_create(C.byref(h), kind, C.byref(cc), C.sizeof(cc), device), "sky_model_create", L)
         self._h = h
         self._ws = None
         self._ws_batch = 0
@@ -89,7 +89,7 @@ class StepEngine:
             assert arena.is_cuda and arena.dtype == torch.float32 and arena.is_contiguous()
             ptr, n, on_dev = arena.data_ptr(), arena.numel(), 1
         _ffi.check(L.sky_model_load_weights(self._h, ptr, n, manifest, len(manifest), on_dev, st),
-                   "sky_model_load_weights")
+                   "sky_model_load_weights", L)
 
     # -- stepping --------------------------------------------------------------------------
     def _workspace(self, batch: int):
@@ -111,7 +111,7 @@ class StepEngine:
         ws = self._workspace(B)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _ffi.check(self._L.sky_model_step(self._h, x_in.data_ptr(), x_out.data_ptr(), B, ws.data_ptr(),
-                                             ws.numel(), st), "sky_model_step")
+                                             ws.numel(), st), "sky_model_step", self._L)
         return x_out
 
     def debug_tensor(self, what: str, shape, batch: int = 1):
@@ -119,7 +119,7 @@ class StepEngine:
         out = torch.empty(shape, dtype=torch.float32, device=f"cuda:{self.device}")
         st = torch.cuda.current_stream(self.device).cuda_stream
         _ffi.check(self._L.sky_model_debug_copy(self._h, what.encode(), out.data_ptr(), out.numel(),
-                                                   self._workspace(batch).data_ptr(), batch, st), "debug_copy")
+                                                   self._workspace(batch).data_ptr(), batch, st), "debug_copy", self._L)
         return out
 
     def debug_set(self, key: str, value: int):
@@ -138,14 +138,14 @@ class StepEngine:
         for i, n in enumerate(names):
             if tags is None or n in tags:
                 mask |= 1 << i
-        _ffi.check(self._L.sky_model_profile_begin(self._h, mask), "profile_begin")
+        _ffi.check(self._L.sky_model_profile_begin(self._h, mask), "profile_begin", self._L)
 
     def profile_end(self):
         """-> {family: (total_ms, launches)} for the families that ran since profile_begin."""
         names = self.profile_tags()
         ms = (C.c_double * len(names))()
         cnt = (C.c_uint64 * len(names))()
-        _ffi.check(self._L.sky_model_profile_end(self._h, ms, cnt, len(names)), "profile_end")
+        _ffi.check(self._L.sky_model_profile_end(self._h, ms, cnt, len(names)), "profile_end", self._L)
         return {n: (ms[i], int(cnt[i])) for i, n in enumerate(names) if cnt[i]}
 
     def close(self):

@@ -36,7 +36,7 @@ def compare_fullsize(y, fx) -> dict:
     f64 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64)).to(dev)
     ref_s, ref_b, ref_l = f64(fx["y_sample"]), f64(fx["y_block"]), f64(fx["y_last"])
     std = f64(fx["y_std"]).clamp_min(1e-30)
-    ys = t[:, ::16, ::16].double()
+    ys = t[:, ::13, ::17].double()
     d = ys - ref_s
     rel = d.pow(2).sum(dim=(1, 2)).sqrt() / ref_s.pow(2).sum(dim=(1, 2)).sqrt()
     nrm = d.pow(2).mean(dim=(1, 2)).sqrt() / std

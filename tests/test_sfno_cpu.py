@@ -132,5 +132,5 @@ def test_full_size_fixtures_match_the_seeded_inputs():
         fx = load_fixture(model)
         x0 = synthetic_state(names, 721, 1440, 0)
         np.testing.assert_array_equal(x0[:, ::64, ::64], fx["x0_sample"])
-        assert fx["y_sample"].shape == (len(names), 46, 90) and np.isfinite(fx["y_block"]).all()
+        assert fx["y_sample"].shape == (len(names), 56, 85) and np.isfinite(fx["y_block"]).all()
         assert (fx["y_std"] > 0).all() and float(fx["oracle_seconds"]) > 1.0

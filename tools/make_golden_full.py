@@ -4,7 +4,8 @@
     python tools/make_golden_full.py sfno       # E=384, L=8: ~10 min
 
 writes tests/golden/{pangu,sfno}_721x1440_seed0.npz holding, per channel,
-  y_sample   y[:, ::16, ::16]                   point values (46 x 90)
+  y_sample   y[:, ::13, ::17]                   point values (56 x 85): strides 13 / 17 are coprime to the 4x4 patch and the 12-token windows, so the
+                                                sample visits every intra-patch position (a stride of 16 saw only position (0, 0))
   y_block    16x16 block means of y[:, :720]    every pixel of rows 0..719 enters exactly one mean (45 x 90)
   y_last     y[:, 720, ::4]                     the odd last latitude row (padding edge of the patch grid)
   y_norm, y_mean, y_std                         per-channel L2 norm / mean / standard deviation of the full field
@@ -21,7 +22,7 @@ import numpy as np, torch
 def summarise(y):
     y = np.asarray(y, dtype=np.float64)
     blk = y[:, :720].reshape(y.shape[0], 45, 16, 90, 16).mean(axis=(2, 4))
-    return dict(y_sample=y[:, ::16, ::16].astype(np.float32), y_block=blk.astype(np.float32),
+    return dict(y_sample=y[:, ::13, ::17].astype(np.float32), y_block=blk.astype(np.float32),
                 y_last=y[:, 720, ::4].astype(np.float32), y_norm=np.sqrt((y ** 2).sum(axis=(1, 2))),
                 y_mean=y.mean(axis=(1, 2)), y_std=y.std(axis=(1, 2)))
 
