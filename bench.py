@@ -131,8 +131,24 @@ def cpu_reference(max_steps: int, budget_s: float = 100.0):
     else:
         import torch
         from oracle.pangu_ref import PanguRef
+        from skyrim_b200.config import pangu_small
         from skyrim_b200.weights import make_pangu_weights
+        # torch's CPU kernels stop scaling on wide hosts (128 threads ran the full step 1.7x SLOWER than 8 threads did in
+        # the build container): pick the fastest thread count among {all, 64, 32, 16} on a 73x1440 band first, then time
+        # REAL full-size steps with it.  `cores` reports the threads actually used.
+        host_threads, best = cores, None
+        band = pangu_small(73, 1440)
+        bref = PanguRef(band, make_pangu_weights(band, 0))
+        bx = torch.from_numpy(synthetic_state(PANGU_CHANNELS, band.nlat, band.nlon, 0))
+        for n in sorted({host_threads, min(host_threads, 64), min(host_threads, 32), min(host_threads, 16)}, reverse=True):
+            torch.set_num_threads(n)
+            bref.step(bx)
+            t0 = time.perf_counter(); bref.step(bx); dtb = time.perf_counter() - t0
+            if best is None or dtb < best[1]:
+                best = (n, dtb)
+        cores = best[0]
         torch.set_num_threads(cores)
+        del bref, bx
         ref = PanguRef(cfg, make_pangu_weights(cfg, 0))
         xt = torch.from_numpy(x0)
         state = {"x": xt}
@@ -140,7 +156,8 @@ def cpu_reference(max_steps: int, budget_s: float = 100.0):
         def step():
             state["x"] = ref.step(state["x"])
         kind, what = "port", (f"oracle/pangu_ref.py (torch fp32 CPU restatement of the reference forward; onnxruntime / "
-                              f"pangu_weather_6.onnx not present on this box), {cores} threads")
+                              f"pangu_weather_6.onnx not present on this box), {cores} of {host_threads} host threads (fastest of "
+                              f"all/64/32/16 on a 73x1440 band)")
     times = []
     t_all = time.perf_counter()
     while len(times) < max(1, max_steps):

@@ -74,6 +74,9 @@ struct EpiCtx {
   uint32_t svec_s;     // shared-space address of bias | gamma | beta, vstride floats apart (LN epilogues)
   int vstride = 512;
   int patch_stride = G2_PATCH_FLOATS * 4;   // bytes between the patches of consecutive warps
+  // per-row-group scratch an epilogue may cache across the n-tiles of one m-tile (EpiQkvWin: destination row of this lane)
+  mutable long long aux_row0 = -1;
+  mutable int aux = 0;
 };
 
 struct AccTmem2 {

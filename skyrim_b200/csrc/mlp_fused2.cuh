@@ -39,19 +39,12 @@ struct Mlp2Cfg {
   // 8 KB like a W1 item and both share ONE ring in consumption order: with separate rings the idle
   // ring's slots hold nothing while the other one starves (measured: the issuer waited 2k cycles per
   // chunk on W2 with 2 slots, profiles/r1_mlp_pair.md).
-#ifdef SKY_MLP_N2_192   // A/B experiment (dev build): two N=192 parts at C=384 -> each hidden k-slice is read twice, not three times
-  static constexpr int N2 = 192;
-#else
+  // (tried in round 2: N2 = 192 at C=384, i.e. two n-parts and 12 KB ring slots -> only 4 slots fit: mlp 5.74 vs 5.20 ms/step)
   static constexpr int N2 = C == 384 ? 128 : 192;
-#endif
   static constexpr int NP = C / N2;
   static constexpr int W2_HALF = N2 / 2 * 128;   // this CTA's N2/2 rows of a (k-block, n-part) item of the W2 image
   static constexpr int SLOT = W1_HALF > W2_HALF ? W1_HALF : W2_HALF;
-#ifdef SKY_MLP_N2_192
-  static constexpr int S = C == 192 ? 8 : 4;
-#else
   static constexpr int S = C == 192 ? 8 : 7;
-#endif
   static constexpr int A_BYTES = NKB * G2_A_BYTES;
   static constexpr int HID_BYTES = HKB * G2_A_BYTES;
   static constexpr int OFF_W = A_BYTES;

@@ -89,6 +89,66 @@ __global__ void __launch_bounds__(256) k_pack_img(PackDesc d, long long total) {
   *reinterpret_cast<uint4*>(d.lo + off) = *reinterpret_cast<uint4*>(l);
 }
 
+// Tiled variant for the packs that TRANSPOSE (the source is contiguous along a row index, not along k): a block moves a
+// 32 (source-contiguous index d) x 64 (k) tile through shared memory, so the reads are 128-byte coalesced along d and
+// every image row receives its 64 k-values as one 128-byte run (hi) + one (lo).  FAST selects which index is d:
+//   1 = r0, 2 = r1, 3 = batch, 4 = (batch, r0) combined (r0 fastest; s_b == R0 * s_r0, e.g. (m, re/im))
+// The generic kernel above wrote 16-byte chunks 128..2048 bytes apart and ran at ~1.8 TB/s (profiles/r2_sfno.md).
+template <int FAST>
+__global__ void __launch_bounds__(256) k_pack_tile(PackDesc d, int ext_d, int n_kb) {
+  __shared__ float tile[32][65];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int dt = blockIdx.x / n_kb, kb = blockIdx.x % n_kb;
+  const int y = blockIdx.y;
+  // decode (b, r1, r0) of element dd of this tile
+  auto coords = [&](int dd, int& b, int& r1, int& r0) {
+    if (FAST == 1) { r0 = dd; r1 = y % d.R1; b = y / d.R1; }
+    else if (FAST == 2) { r1 = dd; r0 = y % d.R0; b = y / d.R0; }
+    else if (FAST == 3) { b = dd; r0 = y % d.R0; r1 = y / d.R0; }
+    else { b = dd / d.R0; r0 = dd % d.R0; r1 = y; }
+  };
+  {
+    const int dd = dt * 32 + tx;
+    int b, r1, r0;
+    coords(dd, b, r1, r0);
+    const long long base = (long long)b * d.s_b + (long long)r1 * d.s_r1 + (long long)r0 * d.s_r0;
+    const float a_sc = (d.aff_mode == 1 && dd < ext_d) ? d.sc[r1] : 1.f, a_sh = (d.aff_mode == 1 && dd < ext_d) ? d.sh[r1] : 0.f;
+#pragma unroll
+    for (int kk = ty; kk < 64; kk += 8) {
+      const int k = kb * 64 + kk;
+      float x = 0.f;
+      if (dd < ext_d && k < d.k_valid) {
+        x = __ldg(d.src + base + (long long)(k >> 1) * d.s_kh + (long long)(k & 1) * d.s_kl);
+        if (d.act == 1) x = gelu_erf(x);
+        if (d.aff_mode == 1) x = x * a_sc + a_sh;
+        else if (d.aff_mode == 2) x = x * d.sc[k] + d.sh[k];
+      }
+      tile[tx][kk] = x;
+    }
+  }
+  __syncthreads();
+  {
+    const int dv = threadIdx.x >> 3, ch = threadIdx.x & 7;
+    const int dd = dt * 32 + dv;
+    if (dd >= ext_d) return;
+    int b, r1, r0;
+    coords(dd, b, r1, r0);
+    const long long r = (long long)r1 * d.R0 + r0;
+    __half h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = tile[dv][ch * 8 + e];
+      h[e] = __float2half_rn(v);
+      l[e] = __float2half_rn(v - __half2float(h[e]));
+    }
+    const int nkb = d.Kp / 64;
+    const size_t off = (size_t)b * (d.rows_pad / 128) * nkb * G2_A_BYTES + ((size_t)(r >> 7) * nkb + kb) * G2_A_BYTES +
+                       sw128_offset((uint32_t)(r & 127), ch);
+    *reinterpret_cast<uint4*>(d.hi + off) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(d.lo + off) = *reinterpret_cast<uint4*>(l);
+  }
+}
+
 // ======================================================================================
 // weights / tables -> 3-term W images  [batch][N/BN][3*Kp/64][BN x 128 B]   ([hi | hi | lo] along K)
 //   mode 0: src[b*s_b + n*s_n + k*s_k]            (n < n_valid, k < k_valid)
@@ -411,7 +471,28 @@ struct SfnoEngine : Engine {
     if (need > im.bytes) { set_error("internal: image buffer too small (%zu > %zu)", need, im.bytes); return SKY_ERR_STATE; }
     const long long total = (long long)batches * R1 * R0 * (d.Kp / 8);
     prof_begin(tag, st);
-    k_pack_img<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, total);
+    // choose the tiled (transposing) kernel when the source is contiguous along a row index rather than along k
+    const int n_kb = d.Kp / 64;
+    const bool k_contig = s_kh == 2 && s_kl == 1;
+    int fast = 0, ext = 0; long long ny = 0;
+    if (!k_contig && !f32) {
+      if (s_r0 == 1 && R0 >= 32) { fast = 1; ext = R0; ny = (long long)batches * R1; }
+      else if (s_r1 == 1 && R1 >= 32) { fast = 2; ext = R1; ny = (long long)batches * R0; }
+      else if (s_b == 1 && batches >= 32) { fast = 3; ext = batches; ny = (long long)R1 * R0; }
+      else if (s_r0 == 1 && s_b == R0 && batches * R0 >= 32) { fast = 4; ext = batches * R0; ny = R1; }
+      if (ny > 65535) fast = 0;
+    }
+    if (fast) {
+      dim3 grid((unsigned)(((ext + 31) / 32) * n_kb), (unsigned)ny);
+      switch (fast) {
+        case 1: k_pack_tile<1><<<grid, 256, 0, st>>>(d, ext, n_kb); break;
+        case 2: k_pack_tile<2><<<grid, 256, 0, st>>>(d, ext, n_kb); break;
+        case 3: k_pack_tile<3><<<grid, 256, 0, st>>>(d, ext, n_kb); break;
+        default: k_pack_tile<4><<<grid, 256, 0, st>>>(d, ext, n_kb); break;
+      }
+    } else {
+      k_pack_img<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, total);
+    }
     prof_end(tag, st);
     count_launch();
     SKY_CUDA_OK(cudaGetLastError());
