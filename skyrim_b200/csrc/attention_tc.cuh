@@ -149,6 +149,25 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
 #define AT_WAIT(bar, parity) mbar_wait_poll(bar, parity)
 #endif
 
+// exp2 of two non-positive arguments on the FMA / ALU pipes (Cody-Waite: x = n + f, |f| <= 0.5, degree-4 polynomial for 2^f,
+// n into the exponent field; max relative error 4e-5, an order below the fp16 rounding P receives next).  The MUFU unit
+// does 16 exp2 per clock and SM; the softmax needs 4.7e9 of them per step, so every second pair of a row goes here.
+__device__ __forceinline__ void ex2_poly_x2(float x0, float x1, float& e0, float& e1) {
+  const uint64_t x = pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
+  const uint64_t t = add_f32x2(x, pack_f32x2(12582912.f, 12582912.f));             // 1.5 * 2^23: round to nearest integer
+  const uint64_t n = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f32x2(n, pack_f32x2(-1.f, -1.f), x);
+  uint64_t p = fma_f32x2(pack_f32x2(0.0096181291f, 0.0096181291f), f, pack_f32x2(0.0555041087f, 0.0555041087f));
+  p = fma_f32x2(p, f, pack_f32x2(0.2402265070f, 0.2402265070f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6931471806f, 0.6931471806f));
+  p = fma_f32x2(p, f, pack_f32x2(1.f, 1.f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // window position (wz, wh, ww, row j) -> natural token of member b, or -1 for a latitude-padding row
 __device__ __forceinline__ long long at_row_token(const Geo& g, int roll, int b, int wz, int wh, int ww, int j) {
   const int wj = j % WW, hj = (j / WW) % WH, zj = j / (WW * WH);
@@ -324,10 +343,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
 
   // Register reallocation: the softmax threads keep a whole 144-wide score row in registers (and want many exponentials in
   // flight); warpgroup 0 (loader, MMA issuer, two idle warps) gives registers up, the softmax warpgroups take them:
-  // 384 x 168 = 64.5 K = 128 x 64 + 256 x 216 + slack.  The roles therefore split HERE, each with its own segment loop;
+  // 384 x 168 = 64.5 K >= 128 x 48 + 256 x 224.  The roles therefore split HERE, each with its own segment loop;
   // one CTA barrier per segment (after the bias expansion, which borrows V slot 0 as staging) keeps them in step.
   if (warp >= 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     for (long long seg0 = n_begin; seg0 < n_end;) {
       AT_SEGMENT_HEAD
       asm volatile("bar.sync 1, 256;" ::: "memory");   // every softmax warp is done with the previous segment's bias
@@ -389,11 +408,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
       if (tok >= 0) {
         uint8_t* row = a.att_img + ((size_t)(tok >> 7) * a.att_nkb + pair) * (size_t)G2_A_BYTES + (size_t)(tok & 127) * 128;
         const uint32_t r7 = (uint32_t)tok & 7u;
+        const uint64_t inv2 = pack_f32x2(prev_inv, prev_inv);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 pk;
-          pk.x = pack_half2(o[8 * c] * prev_inv, o[8 * c + 1] * prev_inv); pk.y = pack_half2(o[8 * c + 2] * prev_inv, o[8 * c + 3] * prev_inv);
-          pk.z = pack_half2(o[8 * c + 4] * prev_inv, o[8 * c + 5] * prev_inv); pk.w = pack_half2(o[8 * c + 6] * prev_inv, o[8 * c + 7] * prev_inv);
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) unpack_f32x2(mul_f32x2(pack_f32x2(o[8 * c + e], o[8 * c + e + 1]), inv2), y[e], y[e + 1]);
+          pk.x = pack_half2(y[0], y[1]); pk.y = pack_half2(y[2], y[3]);
+          pk.z = pack_half2(y[4], y[5]); pk.w = pack_half2(y[6], y[7]);
           *reinterpret_cast<uint4*>(row + ((((uint32_t)(hd * 4 + c)) ^ r7) << 4)) = pk;
         }
       }
@@ -426,15 +449,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
         const int i = kind < 2 ? q * 32 + lane : 128 + (lane & 15);
         const int hd = kind < 2 ? kind : (lane >> 4);
         const uint32_t brow = smem_u32(bias_s) + hd * AT_BIAS_HEAD_B + i * AT_BIAS_LD;
+        const uint64_t sl22 = pack_f32x2(a.sl2, a.sl2);
 #pragma unroll
         for (int c8 = 0; c8 < 18; ++c8) {
           const uint4 bb = lds_b128(brow + c8 * 16);
           const float2 b0 = h2_to_f2(bb.x), b1 = h2_to_f2(bb.y), b2 = h2_to_f2(bb.z), b3 = h2_to_f2(bb.w);
           float* sp = s + 8 * c8;
-          sp[0] = fmaf(sp[0], a.sl2, b0.x); sp[1] = fmaf(sp[1], a.sl2, b0.y);
-          sp[2] = fmaf(sp[2], a.sl2, b1.x); sp[3] = fmaf(sp[3], a.sl2, b1.y);
-          sp[4] = fmaf(sp[4], a.sl2, b2.x); sp[5] = fmaf(sp[5], a.sl2, b2.y);
-          sp[6] = fmaf(sp[6], a.sl2, b3.x); sp[7] = fmaf(sp[7], a.sl2, b3.y);
+          // packed fp32x2 (FFMA2): one instruction per two scores
+          unpack_f32x2(fma_f32x2(pack_f32x2(sp[0], sp[1]), sl22, pack_f32x2(b0.x, b0.y)), sp[0], sp[1]);
+          unpack_f32x2(fma_f32x2(pack_f32x2(sp[2], sp[3]), sl22, pack_f32x2(b1.x, b1.y)), sp[2], sp[3]);
+          unpack_f32x2(fma_f32x2(pack_f32x2(sp[4], sp[5]), sl22, pack_f32x2(b2.x, b2.y)), sp[4], sp[5]);
+          unpack_f32x2(fma_f32x2(pack_f32x2(sp[6], sp[7]), sl22, pack_f32x2(b3.x, b3.y)), sp[6], sp[7]);
           mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(sp[0], sp[1]), fmaxf(sp[2], sp[3])), fmaxf(fmaxf(sp[4], sp[5]), fmaxf(sp[6], sp[7]))));
         }
       }
@@ -442,17 +467,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
       // the previous tile's PV product has finished: its O row is complete and the group's P buffer may be rewritten
       if (have_prev) { AT_WAIT(&o_full[grp], (cnt_a[0] - 1) & 1); tc_fence_after(); }
       AT_T(3);
+      // fetch the previous tile's O row now: the TMEM read overlaps the exponentials below
+      float o[32];
+      const bool do_epi = have_prev && prev_active;
+      if (do_epi) { __syncwarp(); tmem_ld32_nowait(o_t, o); }
       if (active) {
         // P = exp2(s - max) in (0, 1]: un-normalised into the tensor core, 1/sum applied to the 32 outputs of the row
-        float sum0 = 0.f, sum1 = 0.f;
+        uint64_t sum2 = pack_f32x2(0.f, 0.f);
+        const uint64_t nmx2 = pack_f32x2(-mx, -mx);
         const bool second = kind == 2 && lane >= 16;   // left-over tile: head B's lanes own the second K half
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           uint32_t p[16];
 #pragma unroll
           for (int k = 0; k < (c < 4 ? 16 : 8); ++k) {
-            const float e0 = mufu_ex2(s[32 * c + 2 * k] - mx), e1 = mufu_ex2(s[32 * c + 2 * k + 1] - mx);
-            sum0 += e0; sum1 += e1;
+            float d0, d1, e0, e1;
+            unpack_f32x2(add_f32x2(pack_f32x2(s[32 * c + 2 * k], s[32 * c + 2 * k + 1]), nmx2), d0, d1);
+#ifdef SKY_ATTN_POLY
+            if (k & 1) ex2_poly_x2(d0, d1, e0, e1);          // every second pair on the FMA pipe
+            else { e0 = mufu_ex2(d0); e1 = mufu_ex2(d1); }
+#else
+            e0 = mufu_ex2(d0); e1 = mufu_ex2(d1);
+#endif
+            sum2 = add_f32x2(sum2, pack_f32x2(e0, e1));
             p[k] = pack_half2(e0, e1);
           }
           if (kind < 2) {
@@ -465,13 +502,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
             else { tmem_st8(s_t + 64, pa); tmem_st8(s_t + AT_P_COLS + 64, pb); }
           }
         }
-        inv = 1.f / (sum0 + sum1);
+        { float u0, u1; unpack_f32x2(sum2, u0, u1); inv = 1.f / (u0 + u1); }
       }
       AT_T(4);
-      if (have_prev && prev_active) {
-        float o[32];
-        __syncwarp();
-        tmem_ld32_nowait(o_t, o);
+      if (do_epi) {
         tmem_ld_wait();
         epilogue_store(o);
       }
@@ -501,7 +535,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
       seg0 = seg1;
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     for (long long seg0 = n_begin; seg0 < n_end;) {
       AT_SEGMENT_HEAD
       __syncthreads();                                  // the segment's bias is expanded; V slot 0 is free again

@@ -177,12 +177,14 @@ struct EpiF32Batched {
   static constexpr bool kNeedsBias = false;
   float* out; int ldo; long long batch_stride /*floats*/; const float* bias /*may be null*/;
   int n_valid;  // columns >= n_valid are padding and are not stored
+  const float* add = nullptr;   // optional addend with the layout of `out` (residual / positional term): out = acc + bias + add
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtxB& e) const {
     const int rsub4 = e.lane >> 3, c4 = e.lane & 7;
     const int step = 32 * e.nparts;
     const long long rows_left = e.M - e.row0;
     float* xp = out + (size_t)e.batch * batch_stride + e.row0 * ldo + e.n0 + c4 * 4;
+    const float* ap = add ? add + (size_t)e.batch * batch_stride + e.row0 * ldo + e.n0 + c4 * 4 : nullptr;
     for (int c = e.part * 32; c < BN; c += step) {
       float v[32];
       acc.load32(c, v);
@@ -203,11 +205,39 @@ struct EpiF32Batched {
             float4 y = make_float4(lds_f32(pa) + b.x, lds_f32(pa + 4) + b.y, lds_f32(pa + 8) + b.z, lds_f32(pa + 12) + b.w);
             float4* dst = reinterpret_cast<float4*>(xp + (size_t)rr * ldo + c);
             if (kAccumulate) { const float4 o = *dst; y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w; }
+            if (ap) { const float4 o = __ldg(reinterpret_cast<const float4*>(ap + (size_t)rr * ldo + c)); y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w; }
             *dst = y;
           }
         }
       }
       __syncwarp();
+    }
+  }
+};
+
+// Inverse longitude DFT: rows = (lat, c) with c fastest (E channels, E % 32 == 0), columns = lon.  Stores the result
+// PIXEL-MAJOR, out[(lat * W + lon) * E + c], straight from the accumulator registers: lane = row = channel c0 + lane, so for
+// every column (longitude) the warp's 32 lanes hold 32 consecutive channels of ONE pixel = one 128-byte store.
+// Replaces the fp32 [(lat, c)][lon] buffer and the k_transpose pass that used to follow this GEMM.
+struct EpiF32PixelMajor {
+  static constexpr bool kNeedsBias = false;
+  float* out; int E; int W; int n_valid;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtxB& e) const {
+    const long long r0 = e.row0;                       // 32-aligned and E % 32 == 0: the 32 rows share their latitude
+    const bool ok = r0 < e.M;
+    const long long lat = r0 / E;
+    const int c0 = (int)(r0 - lat * E);
+    float* obase = out + (size_t)lat * W * E + c0 + e.lane;
+    for (int c = e.part * 32; c < BN; c += 32 * e.nparts) {
+      float v[32];
+      acc.load32(c, v);
+      if (!ok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int lon = e.n0 + c + j;
+        if (lon < n_valid && c + j < BN) obase[(size_t)lon * E] = v[j];
+      }
     }
   }
 };

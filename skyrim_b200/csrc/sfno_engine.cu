@@ -194,32 +194,38 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
 }
 
 // per-column sums of (optionally GELU'd) fp32 [P, E]:  sums[c], sums[E + c]  (instance norm).
-// Block = (32 column lanes) x (8 row lanes): each thread strides over its rows, the 8 partials
-// of a column meet in shared memory, one fp64 atomic per (block, column).
+// Block = 32 lanes x 8 row-lanes; a lane owns FOUR consecutive columns (128-bit loads: a warp reads 512 contiguous
+// bytes of a row), strides over its rows, the 8 partials of a column meet in shared memory, one fp64 atomic per
+// (block, column).  E % 4 == 0.
 __global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ x, long long P, int E, int act,
                                                   double* __restrict__ sums, int rows_per_block) {
-  __shared__ float red[2][8][33];
+  __shared__ float4 red[2][8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
-  const int c = blockIdx.x * 32 + cx;
-  float s = 0.f, ss = 0.f;
+  const int c = (blockIdx.x * 32 + cx) * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
   if (c < E) {
-    for (int i = ry; i < rows_per_block; i += 8) {
-      const long long r = r0 + i;
-      if (r >= P) break;
-      float v = x[r * E + c];
-      if (act) v = gelu_erf(v);
-      s += v; ss += v * v;
+    long long rend = r0 + rows_per_block;
+    if (rend > P) rend = P;
+#pragma unroll 4
+    for (long long r = r0 + ry; r < rend; r += 8) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + r * E + c));
+      if (act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
     }
   }
   red[0][ry][cx] = s; red[1][ry][cx] = ss;
   __syncthreads();
   if (ry == 0 && c < E) {
-    float a = 0.f, b = 0.f;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a += red[0][i][cx]; b += red[1][i][cx]; }
-    atomicAdd(&sums[c], (double)a);
-    atomicAdd(&sums[E + c], (double)b);
+    for (int i = 0; i < 8; ++i) {
+      const float4 u = red[0][i][cx], w = red[1][i][cx];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w; b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+    }
+    atomicAdd(&sums[c], (double)a.x); atomicAdd(&sums[c + 1], (double)a.y); atomicAdd(&sums[c + 2], (double)a.z); atomicAdd(&sums[c + 3], (double)a.w);
+    atomicAdd(&sums[E + c], (double)b.x); atomicAdd(&sums[E + c + 1], (double)b.y); atomicAdd(&sums[E + c + 2], (double)b.z); atomicAdd(&sums[E + c + 3], (double)b.w);
   }
 }
 // sc = gamma * rstd, sh = beta - mean * sc
@@ -307,7 +313,7 @@ struct SfnoEngine : Engine {
   float *in_sc, *in_sh, *n_sc, *n_sh;
   double* sums;
   // scratch (engine owned, one member at a time)
-  float *X, *Xn, *F1, *Fd, *Fl, *Fs, *G, *Fx, *Rpm;
+  float *X, *Xn, *F1, *Fd, *Fl, *Fs, *G, *Rpm;
   Img2 I_a, I_b, I_cm, I_in, I_leg, I_spec, I_ileg, I_idft;
   bool scratch_ready = false;
 
@@ -439,8 +445,7 @@ struct SfnoEngine : Engine {
     Fl = dalloc<float>((size_t)mmax * 2 * E * lmax);
     Fs = dalloc<float>((size_t)lmax * pad_to(mmax, 128) * 2 * E);
     G = dalloc<float>((size_t)mmax * 2 * E * latp1);
-    Fx = dalloc<float>((size_t)H1 * E * W1);
-    if (!X || !Xn || !F1 || !Rpm || !Fd || !Fl || !Fs || !G || !Fx) return SKY_ERR_NOMEM;
+    if (!X || !Xn || !F1 || !Rpm || !Fd || !Fl || !Fs || !G) return SKY_ERR_NOMEM;
     const size_t ab = img_bytes(P1, (int)Hd);
     if (!img_alloc(I_a, ab) || !img_alloc(I_b, ab)) return SKY_ERR_NOMEM;
     if (!img_alloc(I_in, img_bytes(P1, Cin))) return SKY_ERR_NOMEM;
@@ -527,14 +532,15 @@ struct SfnoEngine : Engine {
     return rc;
   }
   int gemm(int tag, const Img2& A, int K, long long a_bstride_bytes, long long rows_per_batch, float* out, int ldo,
-           long long out_bstride, const float* bias, bool accumulate, const W3& w, long long M, cudaStream_t st) {
+           long long out_bstride, const float* bias, bool accumulate, const W3& w, long long M, cudaStream_t st,
+           const float* add = nullptr) {
     const int nkb = pad_to(K, 64) / 64;
     const int mt = pad_to((int)rows_per_batch, 128) / 128;
     if (accumulate) {
-      EpiF32Batched<true> e{out, ldo, out_bstride, bias, w.N};
+      EpiF32Batched<true> e{out, ldo, out_bstride, bias, w.N, add};
       return gemm_epi(tag, A, nkb, a_bstride_bytes, mt, e, w, M, st);
     }
-    EpiF32Batched<false> e{out, ldo, out_bstride, bias, w.N};
+    EpiF32Batched<false> e{out, ldo, out_bstride, bias, w.N, add};
     return gemm_epi(tag, A, nkb, a_bstride_bytes, mt, e, w, M, st);
   }
 
@@ -552,8 +558,8 @@ struct SfnoEngine : Engine {
   int norm_stats(const float* x, long long P, int act, const float* g, const float* b, cudaStream_t st) {
     prof_begin(KT_SFNO_MISC, st);
     SKY_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * E * sizeof(double), st));
-    const int rpb = 512;
-    dim3 grid((unsigned)((E + 31) / 32), (unsigned)((P + rpb - 1) / rpb));
+    const int rpb = 256;
+    dim3 grid((unsigned)((E / 4 + 31) / 32), (unsigned)((P + rpb - 1) / rpb));
     k_colstats<<<grid, 256, 0, st>>>(x, P, E, act, sums, rpb);
     k_finalize_norm<<<(E + 127) / 128, 128, 0, st>>>(sums, g, b, cfg.eps, P, E, n_sc, n_sh);
     prof_end(KT_SFNO_MISC, st);
@@ -579,15 +585,13 @@ struct SfnoEngine : Engine {
     if ((rc = gemm(KT_SFNO_ISHT, I_ileg, lmax, a_bs, n2, G, wl.N, (long long)n2 * wl.N, nullptr, false, wl, n2, st))) return rc;
     // A operand of the inverse DFT: rows (lat, c), cols (m, ri):  G[m][(c,ri)][lat]
     if ((rc = pack(KT_SFNO_ISHT, G, I_idft, 1, Ho, E, 2 * mmax, 0, 1, 2LL * wl.N, (long long)n2 * wl.N, wl.N, 0, nullptr, nullptr, 0, 2, 1, 0, 3, st))) return rc;
-    // Fx[(lat, c)][lon]
-    if ((rc = gemm(KT_SFNO_ISHT, I_idft, 2 * mmax, 0, (long long)Ho * E, Fx, Wo, 0, nullptr, false, wd, (long long)Ho * E, st))) return rc;
-    // -> pixel major [(lat, lon)][c]
-    prof_begin(KT_SFNO_ISHT, st);
-    dim3 g((unsigned)((Wo + 31) / 32), (unsigned)((E + 31) / 32), (unsigned)Ho), bdim(32, 8);
-    k_transpose<<<g, bdim, 0, st>>>(Fx, out_pm, E, Wo, accumulate ? 1 : 0);
-    prof_end(KT_SFNO_ISHT, st);
-    count_launch();
-    SKY_CUDA_OK(cudaGetLastError());
+    // inverse longitude DFT, stored pixel-major [(lat, lon)][c] by the epilogue (no Fx buffer, no transpose pass)
+    if (accumulate || E % 32) { set_error("internal: inverse_sht accumulate / E %% 32"); return SKY_ERR_STATE; }
+    {
+      EpiF32PixelMajor e{out_pm, E, Wo, Wo};
+      const int nkb = pad_to(2 * mmax, 64) / 64, mt = pad_to((int)((long long)Ho * E), 128) / 128;
+      if ((rc = gemm_epi(KT_SFNO_ISHT, I_idft, nkb, 0, mt, e, wd, (long long)Ho * E, st))) return rc;
+    }
     return 0;
   }
 
@@ -629,9 +633,8 @@ struct SfnoEngine : Engine {
     if ((rc = pack(KT_SFNO_MLP, F1, I_b, 1, 1, (int)Po, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 1, 0, 1, 2, 3, st))) return rc;
     // GELU(fc1) goes straight into the operand images of fc2 (I_a: the residual image it held was consumed by the inner skip)
     if ((rc = gemm_to_img(KT_SFNO_MLP, I_b, E, Po, I_a, Hd, b.fc1_b, true, b.fc1, st))) return rc;
-    // x_out = residual + fc2(...)   (accumulate onto a copy of the residual)
-    SKY_CUDA_OK(cudaMemcpyAsync(xout, Rpm, (size_t)Po * E * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = gemm(KT_SFNO_MLP, I_a, Hd, 0, Po, xout, E, 0, b.fc2_b, true, b.fc2, Po, st))) return rc;
+    // x_out = residual + fc2(...): the residual is an addend of the epilogue (no copy, no read-modify-write)
+    if ((rc = gemm(KT_SFNO_MLP, I_a, Hd, 0, Po, xout, E, 0, b.fc2_b, false, b.fc2, Po, st, Rpm))) return rc;
     float* tmp = xin; xin = xout; xout = tmp;
     return 0;
   }
@@ -641,8 +644,7 @@ struct SfnoEngine : Engine {
     // encoder
     if ((rc = pack(KT_SFNO_ENC, x_in, I_in, 1, 1, (int)P1, Cin, 0, 0, 1, 2LL * P1, P1, 2, in_sc, in_sh, 0, 1, 0, 2, 3, st))) return rc;
     if ((rc = gemm_to_img(KT_SFNO_ENC, I_in, Cin, P1, I_a, E, enc1_b, true, enc1, st))) return rc;   // GELU(fc1) -> split images
-    SKY_CUDA_OK(cudaMemcpyAsync(X, pos_pm, (size_t)P1 * E * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = gemm(KT_SFNO_ENC, I_a, E, 0, P1, X, E, 0, enc2_b, true, enc2, P1, st))) return rc;
+    if ((rc = gemm(KT_SFNO_ENC, I_a, E, 0, P1, X, E, 0, enc2_b, false, enc2, P1, st, pos_pm))) return rc;   // + positional embedding
     float *a = X, *b = Xn;
     for (int i = 0; i < L; ++i)
       if ((rc = run_block(i, a, b, st))) return rc;

@@ -18,7 +18,53 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+void Engine::drop_graphs() {
+  for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  graphs.clear();
+}
+
+int Engine::step_cached(const float* x_in, float* x_out, int batch, void* ws, size_t ws_bytes, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (!use_graphs || prof_mask != 0 || stop_after != 99 || cudaStreamIsCapturing(st, &cs) != cudaSuccess ||
+      cs != cudaStreamCaptureStatusNone)
+    return step(x_in, x_out, batch, ws, ws_bytes, st);
+  GraphEntry* e = nullptr;
+  for (auto& g : graphs)
+    if (g.x_in == x_in && g.x_out == x_out && g.ws == ws && g.batch == batch) { e = &g; break; }
+  if (e && e->exec) {
+    SKY_CUDA_OK(cudaGraphLaunch(e->exec, st));
+    count_launch((int)e->launches);
+    return 0;
+  }
+  if (!e) {   // first sight of this tuple: run eagerly (opt-ins and lazy set-up happen here), remember it
+    if (graphs.size() >= 8) { if (graphs.front().exec) cudaGraphExecDestroy(graphs.front().exec); graphs.erase(graphs.begin()); }
+    graphs.push_back(GraphEntry{x_in, x_out, ws, batch, nullptr, 0, 1});
+    return step(x_in, x_out, batch, ws, ws_bytes, st);
+  }
+  // second call: capture the launch sequence, instantiate, launch
+  const uint64_t l0 = g_launches.load();
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return step(x_in, x_out, batch, ws, ws_bytes, st); }
+  const int rc = step(x_in, x_out, batch, ws, ws_bytes, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    use_graphs = false;                       // never retry; fall back to plain launches
+    return rc ? rc : step(x_in, x_out, batch, ws, ws_bytes, st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) { cudaGetLastError(); use_graphs = false; return step(x_in, x_out, batch, ws, ws_bytes, st); }
+  e->exec = exec;
+  e->launches = g_launches.load() - l0;       // kernels recorded by the capture (they did not run yet)
+  SKY_CUDA_OK(cudaGraphLaunch(exec, st));
+  return 0;
+}
+
 Engine::~Engine() {
+  drop_graphs();
   if (arena) cudaFree(arena);
   for (void* p : kept) cudaFree(p);
   for (auto e : prof_pool) cudaEventDestroy(e);
@@ -53,6 +99,7 @@ int Engine::prof_collect(double* ms, uint64_t* counts, int n) {
 
 int Engine::load_arena(const float* src, uint64_t n_floats, const sky_param_desc_t* manifest, int n_params,
                        int on_device, cudaStream_t st) {
+  drop_graphs();
   if (arena) { cudaFree(arena); arena = nullptr; }
   for (void* p : kept) cudaFree(p);
   kept.clear();
@@ -95,6 +142,7 @@ const float* Engine::keep(const char* name, uint64_t expect, cudaStream_t st) {
 
 int Engine::debug_set(const char* key, long long value) {
   if (!strcmp(key, "stop_after")) { stop_after = (int)value; return 0; }
+  if (!strcmp(key, "use_graphs")) { use_graphs = value != 0; return 0; }
   set_error("unknown debug key '%s'", key);
   return SKY_ERR_ARG;
 }
@@ -216,7 +264,7 @@ int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batc
   if (!m || !x_in || !x_out || !ws || batch <= 0) { set_error("bad argument"); return SKY_ERR_ARG; }
   if (x_in == x_out) { set_error("x_in and x_out may not alias"); return SKY_ERR_ARG; }
   DeviceGuard guard(m->eng->device);
-  return m->eng->step(x_in, x_out, batch, ws, ws_bytes, (cudaStream_t)stream);
+  return m->eng->step_cached(x_in, x_out, batch, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* ws, int32_t batch,
