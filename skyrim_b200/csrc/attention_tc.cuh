@@ -143,30 +143,22 @@ __device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 #ifdef SKY_ATTN_WAIT_SUSPEND
 #define AT_WAIT(bar, parity) mbar_wait(bar, parity)
 #else
 #define AT_WAIT(bar, parity) mbar_wait_poll(bar, parity)
 #endif
-
-// exp2 of two non-positive arguments on the FMA / ALU pipes (Cody-Waite: x = n + f, |f| <= 0.5, degree-4 polynomial for 2^f,
-// n into the exponent field; max relative error 4e-5, an order below the fp16 rounding P receives next).  The MUFU unit
-// does 16 exp2 per clock and SM; the softmax needs 4.7e9 of them per step, so every second pair of a row goes here.
-__device__ __forceinline__ void ex2_poly_x2(float x0, float x1, float& e0, float& e1) {
-  const uint64_t x = pack_f32x2(fmaxf(x0, -120.f), fmaxf(x1, -120.f));
-  const uint64_t t = add_f32x2(x, pack_f32x2(12582912.f, 12582912.f));             // 1.5 * 2^23: round to nearest integer
-  const uint64_t n = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
-  const uint64_t f = fma_f32x2(n, pack_f32x2(-1.f, -1.f), x);
-  uint64_t p = fma_f32x2(pack_f32x2(0.0096181291f, 0.0096181291f), f, pack_f32x2(0.0555041087f, 0.0555041087f));
-  p = fma_f32x2(p, f, pack_f32x2(0.2402265070f, 0.2402265070f));
-  p = fma_f32x2(p, f, pack_f32x2(0.6931471806f, 0.6931471806f));
-  p = fma_f32x2(p, f, pack_f32x2(1.f, 1.f));
-  float p0, p1, t0, t1;
-  unpack_f32x2(p, p0, p1);
-  unpack_f32x2(t, t0, t1);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
 
 // window position (wz, wh, ww, row j) -> natural token of member b, or -1 for a latitude-padding row
 __device__ __forceinline__ long long at_row_token(const Geo& g, int roll, int b, int wz, int wh, int ww, int j) {
@@ -483,12 +475,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_window_attention_tc(const Att
           for (int k = 0; k < (c < 4 ? 16 : 8); ++k) {
             float d0, d1, e0, e1;
             unpack_f32x2(add_f32x2(pack_f32x2(s[32 * c + 2 * k], s[32 * c + 2 * k + 1]), nmx2), d0, d1);
-#ifdef SKY_ATTN_POLY
-            if (k & 1) ex2_poly_x2(d0, d1, e0, e1);          // every second pair on the FMA pipe
-            else { e0 = mufu_ex2(d0); e1 = mufu_ex2(d1); }
-#else
             e0 = mufu_ex2(d0); e1 = mufu_ex2(d1);
-#endif
             sum2 = add_f32x2(sum2, pack_f32x2(e0, e1));
             p[k] = pack_half2(e0, e1);
           }
