@@ -111,21 +111,27 @@ class GlobalModel:
         vals = np.asarray(ic.values, dtype=np.float32)
         vals = vals[-1] if vals.ndim == 4 else vals
         x = torch.from_numpy(np.ascontiguousarray(vals))[None, None]
-        gen = self.model(start_time, x)
+        if save and hasattr(self.model, "iter_host"):
+            # every state is needed on the host: device->host copy of step n overlaps step n+1 (timeloop.iter_host)
+            gen = ((t, h[0].numpy(), None) for t, h in self.model.iter_host(start_time, x, n_steps))
+            to_host = lambda a: a
+        else:
+            gen = self.model(start_time, x)
+            to_host = lambda a: a.cpu().numpy()[0]
         t_prev, prev, _ = next(gen)
-        prev_host = prev.cpu().numpy()[0]
+        prev_host = np.array(to_host(prev))   # own copy: the iterator's host buffers are a ring of two
         for n in range(n_steps):
             t_cur, cur, _ = next(gen)
             need_host = save or n == n_steps - 1
             if need_host:
-                cur_host = cur.cpu().numpy()[0]
+                cur_host = to_host(cur)
                 pred = xr.DataArray(np.stack([prev_host, cur_host]), dims=["time", "channel", "lat", "lon"],
                                     coords=dict(time=np.array([np.datetime64(t_prev, "s"), np.datetime64(t_cur, "s")]),
                                                 channel=np.array(self.out_channel_names),
                                                 lat=np.array(self.model.grid.lat), lon=np.array(self.model.grid.lon)))
                 if save:
                     output_paths.append(save_forecast(pred, self.model_name, t_prev, t_cur, source, config=save_config))
-                prev_host = cur_host
+                prev_host = pred.values[1]
             t_prev, source = t_cur, "file"
             logger.success(f"Rollout step {n+1}/{n_steps} completed")
         return pred, output_paths

@@ -186,15 +186,33 @@ struct EpiF32Batched {
     float* xp = out + (size_t)e.batch * batch_stride + e.row0 * ldo + e.n0 + c4 * 4;
     const float* ap = add ? add + (size_t)e.batch * batch_stride + e.row0 * ldo + e.n0 + c4 * 4 : nullptr;
     for (int c = e.part * 32; c < BN; c += step) {
-      float v[32];
-      acc.load32(c, v);
-      patch_put_s(e.patch_s, e.lane, v);
-      __syncwarp();
       const int col = e.n0 + c + c4 * 4;
       // BN need not be a multiple of 32 (16, 80, 240): the 32-column TMEM read then runs past the tile; those columns
       // belong to the NEXT n-tile (another CTA's work) and must not be stored from here (round-1 bug: they were, and
       // raced with the owner's store whenever N had more than one such tile, e.g. nlon = 1440 or lmax = 240)
-      if (col < n_valid && c + c4 * 4 < BN) {
+      const bool act = col < n_valid && c + c4 * 4 < BN;
+      // all global reads of the chunk (previous value / addend) are issued before the accumulator fetch: written as
+      // load -> add -> store per row they serialise into 8 DRAM round trips per chunk, because the compiler may not move
+      // a load above the preceding store to `out` (ncu r2a: 82 % long-scoreboard stalls, 33 k cycles per 128x192 tile
+      // against 7 k of MMA time)
+      float4 o[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        o[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act && rr < rows_left) {
+          if (kAccumulate) o[it] = *reinterpret_cast<const float4*>(xp + (size_t)rr * ldo + c);
+          if (ap) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(ap + (size_t)rr * ldo + c));
+            o[it].x += a.x; o[it].y += a.y; o[it].z += a.z; o[it].w += a.w;
+          }
+        }
+      }
+      float v[32];
+      acc.load32(c, v);
+      patch_put_s(e.patch_s, e.lane, v);
+      __syncwarp();
+      if (act) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + col));
 #pragma unroll
@@ -202,11 +220,9 @@ struct EpiF32Batched {
           const int rr = it * 4 + rsub4;
           if (rr < rows_left) {
             const uint32_t pa = e.patch_s + (rr * G2_PATCH_LD + c4 * 4) * 4;
-            float4 y = make_float4(lds_f32(pa) + b.x, lds_f32(pa + 4) + b.y, lds_f32(pa + 8) + b.z, lds_f32(pa + 12) + b.w);
-            float4* dst = reinterpret_cast<float4*>(xp + (size_t)rr * ldo + c);
-            if (kAccumulate) { const float4 o = *dst; y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w; }
-            if (ap) { const float4 o = __ldg(reinterpret_cast<const float4*>(ap + (size_t)rr * ldo + c)); y.x += o.x; y.y += o.y; y.z += o.z; y.w += o.w; }
-            *dst = y;
+            const float4 y = make_float4(lds_f32(pa) + b.x + o[it].x, lds_f32(pa + 4) + b.y + o[it].y,
+                                         lds_f32(pa + 8) + b.z + o[it].z, lds_f32(pa + 12) + b.w + o[it].w);
+            *reinterpret_cast<float4*>(xp + (size_t)rr * ldo + c) = y;
           }
         }
       }
@@ -222,6 +238,7 @@ struct EpiF32Batched {
 struct EpiF32PixelMajor {
   static constexpr bool kNeedsBias = false;
   float* out; int E; int W; int n_valid;
+  const float* chan_bias = nullptr;   // optional per-channel constant (the folded inner skip's bias)
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtxB& e) const {
     const long long r0 = e.row0;                       // 32-aligned and E % 32 == 0: the 32 rows share their latitude
@@ -229,6 +246,7 @@ struct EpiF32PixelMajor {
     const long long lat = r0 / E;
     const int c0 = (int)(r0 - lat * E);
     float* obase = out + (size_t)lat * W * E + c0 + e.lane;
+    const float cb = (chan_bias && ok) ? __ldg(chan_bias + c0 + e.lane) : 0.f;
     for (int c = e.part * 32; c < BN; c += 32 * e.nparts) {
       float v[32];
       acc.load32(c, v);
@@ -236,7 +254,7 @@ struct EpiF32PixelMajor {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int lon = e.n0 + c + j;
-        if (lon < n_valid && c + j < BN) obase[(size_t)lon * E] = v[j];
+        if (lon < n_valid && c + j < BN) obase[(size_t)lon * E] = v[j] + cb;
       }
     }
   }

@@ -197,6 +197,16 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
 // Block = 32 lanes x 8 row-lanes; a lane owns FOUR consecutive columns (128-bit loads: a warp reads 512 contiguous
 // bytes of a row), strides over its rows, the 8 partials of a column meet in shared memory, one fp64 atomic per
 // (block, column).  E % 4 == 0.
+// Grid-changing blocks (first: 721x1440 -> 240x480, last: back): the inner skip acts on residual = iSHT(X), X the block's
+// own forward spectrum, and a 1x1 convolution commutes with the (linear, per-channel) inverse transform:
+//   iSHT(W_l X) + V iSHT(X) = iSHT((W_l + V) X)
+// so V is added to the real part of every degree's mixing matrix once, at load time, and the pixel-space GEMM over the
+// output grid (1.04 M pixels for the last block) and the operand pack feeding it disappear.  spec: (l, out, in, re/im).
+__global__ void k_fold_inner_into_spec(float* __restrict__ spec, const float* __restrict__ inner, long long total, int EE) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) spec[2 * i] += inner[i % EE];
+}
+
 __global__ void __launch_bounds__(256) k_colstats(const float* __restrict__ x, long long P, int E, int act,
                                                   double* __restrict__ sums, int rows_per_block) {
   __shared__ float4 red[2][8][33];
@@ -410,10 +420,18 @@ struct SfnoEngine : Engine {
       auto N = [&](const char* s) { snprintf(nm, sizeof nm, "blk%d.%s", i, s); return nm; };
       const float* w;
       KEEP(b.n0g, N("norm0.g"), E); KEEP(b.n0b, N("norm0.b"), E); KEEP(b.n1g, N("norm1.g"), E); KEEP(b.n1b, N("norm1.b"), E);
+      const float* wi;
       P(w, N("spec.w"), (long long)lmax * E * E * 2);
+      P(wi, N("inner.w"), (long long)E * E); KEEP(b.inner_b, N("inner.b"), E);
+      if ((i == 0) != (i == L - 1)) {   // grid-changing block (run_block: Hi != Ho): inner skip folded into the mixing matrices
+        const long long total = (long long)lmax * E * E;
+        k_fold_inner_into_spec<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(const_cast<float*>(w), wi, total, E * E);
+        count_launch();
+        SKY_CUDA_OK(cudaGetLastError());
+      } else {
+        if ((rc = pack_w(b.inner, wi, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
+      }
       if ((rc = pack_w(b.spec, w, 1, 2 * E, 2 * E, 2 * E, bn_point(2 * E), lmax, 0, 0, 0, st))) return rc;
-      P(w, N("inner.w"), (long long)E * E); KEEP(b.inner_b, N("inner.b"), E);
-      if ((rc = pack_w(b.inner, w, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
       const int Hd = cfg.mlp_ratio * E;
       P(w, N("fc1.w"), (long long)Hd * E); KEEP(b.fc1_b, N("fc1.b"), Hd);
       if ((rc = pack_w(b.fc1, w, 0, Hd, E, Hd, bn_point(Hd), 1, 0, E, 1, st))) return rc;
@@ -570,7 +588,7 @@ struct SfnoEngine : Engine {
 
   // inverse SHT of coefficient tensor `coef` (indexed [m][n=(c,ri)][l] when from_legendre, or
   // [l][m][n] when from the spectral mixing) onto grid (Ho, Wo) -> pixel-major fp32 [Ho*Wo, E]
-  int inverse_sht(const float* coef, bool from_legendre, int Ho, int Wo, float* out_pm, bool accumulate, cudaStream_t st) {
+  int inverse_sht(const float* coef, bool from_legendre, int Ho, int Wo, float* out_pm, const float* chan_bias, cudaStream_t st) {
     const int n2 = 2 * E, lp = pad_to(lmax, 64);
     const bool big = Ho == H1;
     const W3& wl = big ? legi_big : legi_int;
@@ -586,9 +604,9 @@ struct SfnoEngine : Engine {
     // A operand of the inverse DFT: rows (lat, c), cols (m, ri):  G[m][(c,ri)][lat]
     if ((rc = pack(KT_SFNO_ISHT, G, I_idft, 1, Ho, E, 2 * mmax, 0, 1, 2LL * wl.N, (long long)n2 * wl.N, wl.N, 0, nullptr, nullptr, 0, 2, 1, 0, 3, st))) return rc;
     // inverse longitude DFT, stored pixel-major [(lat, lon)][c] by the epilogue (no Fx buffer, no transpose pass)
-    if (accumulate || E % 32) { set_error("internal: inverse_sht accumulate / E %% 32"); return SKY_ERR_STATE; }
+    if (E % 32) { set_error("internal: inverse_sht needs E %% 32 == 0"); return SKY_ERR_STATE; }
     {
-      EpiF32PixelMajor e{out_pm, E, Wo, Wo};
+      EpiF32PixelMajor e{out_pm, E, Wo, Wo, chan_bias};
       const int nkb = pad_to(2 * mmax, 64) / 64, mt = pad_to((int)((long long)Ho * E), 128) / 128;
       if ((rc = gemm_epi(KT_SFNO_ISHT, I_idft, nkb, 0, mt, e, wd, (long long)Ho * E, st))) return rc;
     }
@@ -617,8 +635,8 @@ struct SfnoEngine : Engine {
     if (Hi == Ho) {
       if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st, Rpm, E))) return rc;
     } else {
-      if ((rc = inverse_sht(Fl, true, Ho, Wo, Rpm, false, st))) return rc;
-      if ((rc = pack(KT_SFNO_MISC, Rpm, I_a, 1, 1, (int)Po, E, 0, 0, E, 2, 1, 0, nullptr, nullptr, 0, 0, 1, 2, 3, st))) return rc;
+      // only the OUTER skip needs the resampled residual as a field; the inner skip lives in the mixing matrices
+      if ((rc = inverse_sht(Fl, true, Ho, Wo, Rpm, nullptr, st))) return rc;
     }
     // spectral channel mixing, one GEMM per degree l: rows m, K = (i, ri):  Fl[m][(i,ri)][l]
     if ((rc = pack(KT_SFNO_SPEC, Fl, I_spec, lmax, 1, mmax, n2, 1, 0, (long long)n2 * lmax, 2LL * lmax, lmax, 0, nullptr, nullptr, 0, 3, 0, 1, 2, st))) return rc;
@@ -626,8 +644,12 @@ struct SfnoEngine : Engine {
     const long long spec_bs = (long long)(mp / 128) * (pad_to(n2, 64) / 64) * G2_A_BYTES;
     if ((rc = gemm(KT_SFNO_SPEC, I_spec, n2, spec_bs, mmax, Fs, n2, (long long)mp * n2, nullptr, false, b.spec, mmax, st))) return rc;
     // y = iSHT(mixed) + inner_skip(residual) + bias  (pixel-major fp32 in F1)
-    if ((rc = inverse_sht(Fs, false, Ho, Wo, F1, false, st))) return rc;
-    if ((rc = gemm(KT_SFNO_MLP, I_a, E, 0, Po, F1, E, 0, b.inner_b, true, b.inner, Po, st))) return rc;
+    if (Hi == Ho) {
+      if ((rc = inverse_sht(Fs, false, Ho, Wo, F1, nullptr, st))) return rc;
+      if ((rc = gemm(KT_SFNO_MLP, I_a, E, 0, Po, F1, E, 0, b.inner_b, true, b.inner, Po, st))) return rc;
+    } else {
+      if ((rc = inverse_sht(Fs, false, Ho, Wo, F1, b.inner_b, st))) return rc;   // folded inner skip: only its bias is left
+    }
     // norm1(GELU(y)) -> MLP
     if ((rc = norm_stats(F1, Po, 1, b.n1g, b.n1b, st))) return rc;
     if ((rc = pack(KT_SFNO_MLP, F1, I_b, 1, 1, (int)Po, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 1, 0, 1, 2, 3, st))) return rc;

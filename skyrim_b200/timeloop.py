@@ -72,6 +72,39 @@ class _EngineTimeLoop:
             yield time, nxt, None
             cur, nxt = nxt, torch.empty_like(cur)  # the yielded tensor stays valid for the caller
 
+    def iter_host(self, time, x, n_steps: int):
+        """Rollout with every state delivered to the HOST: yields (time, pinned fp32 tensor (B, C, H, W)) for the initial
+        condition and then for each of ``n_steps`` 6-h steps.  The state stays in HBM; the device->host copy of step n runs on
+        a copy stream while step n+1 computes (a ring of three device states: n+1 is written while n is read by both the
+        copy and the step).  A yielded host tensor is valid until the second next() after it (ring of two).
+        ``GlobalModel.rollout(save=True)`` consumes this instead of ``.cpu()`` per step (base.py:131-141 in the reference)."""
+        torch = self.torch
+        assert x.dim() == 5 and x.shape[1] == self.n_history_levels, x.shape
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        shape = (x.shape[0],) + tuple(x.shape[2:])
+        if getattr(self, "_ring", None) is None or tuple(self._ring[0].shape) != shape:
+            self._ring = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(3)]
+            self._host_ring = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+        ring, host = self._ring, self._host_ring
+        ring[0].copy_(x[:, -1].to(dtype=torch.float32), non_blocking=True)
+        done = [torch.cuda.Event() for _ in range(3)]     # state i is complete on the main stream
+        copied = torch.cuda.Event()
+        done[0].record(main)
+        if n_steps > 0:
+            self.engine.step(ring[0], ring[1]); done[1].record(main)
+        for n in range(n_steps + 1):
+            if 0 < n < n_steps:   # launch step n+1 before waiting for the copy of step n
+                self.engine.step(ring[n % 3], ring[(n + 1) % 3]); done[(n + 1) % 3].record(main)
+            self._copy_stream.wait_event(done[n % 3])
+            with torch.cuda.stream(self._copy_stream):
+                host[n % 2].copy_(ring[n % 3], non_blocking=True)
+                copied.record(self._copy_stream)
+            copied.synchronize()   # also orders the overwrite of ring[n % 3] (three steps from now) after this copy
+            yield time, host[n % 2]
+            time = time + self.time_step
+
     def step_host(self, x_host):
         """One step with HOST (pinned) input and HOST (pinned) output — the end-to-end unit that
         bench.py's ``e2e`` times: H2D of the state, sky_model_step, D2H of the result."""

@@ -34,3 +34,30 @@ def test_pangu_predict_api(tmp_path):
     da = sk.forecast(datetime.datetime(2024, 5, 7), n_steps=2, channels=["t2m", "u10m"])
     assert da.shape == (3, 2, 41, 96)
     np.testing.assert_allclose(da.values[0, 0], x0[PANGU_CHANNELS.index("t2m")])
+
+
+def test_iter_host_matches_device_resident_chain():
+    """Overlapped host delivery (copy of step n under step n+1, ring of three device states, graph replay from the third
+    use of a pair) returns bit-identical states to a plain chain of steps."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from skyrim_b200.config import PANGU_CHANNELS, pangu_small
+    from skyrim_b200.engine import StepEngine
+    from skyrim_b200.timeloop import PanguTimeLoop
+    from skyrim_b200.weights import make_pangu_weights, synthetic_state
+    cfg = pangu_small(41, 96)
+    eng = StepEngine(cfg, 0)
+    eng.load_weights(make_pangu_weights(cfg, 0))
+    x0 = torch.from_numpy(synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0))[None]
+    loop = PanguTimeLoop(eng)
+    t0 = datetime.datetime(2024, 5, 7)
+    want, cur = [x0.clone()], x0.cuda()
+    for _ in range(7):
+        cur = eng.step(cur)
+        want.append(cur.cpu())
+    for rep in range(2):   # second pass runs on the replayed graphs
+        got = [(t, h.clone()) for t, h in loop.iter_host(t0, x0[:, None], 7)]
+        assert len(got) == 8 and got[3][0] == t0 + 3 * loop.time_step
+        for (t, h), w in zip(got, want):
+            assert torch.equal(h, w)
+    eng.close()

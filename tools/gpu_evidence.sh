@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round-end evidence on one B200 (run through gpurun): the bench line, the ncu launch lists of the bench command, and
+# `ncu --set full` captures of the dominant kernels.  Everything lands in gpurun_out/; the summaries are copied to profiles/.
+tag=${1:-r2}
+mkdir -p gpurun_out
+python bench.py > gpurun_out/${tag}_bench_final.json 2> gpurun_out/${tag}_bench_final.err
+echo "bench rc=$?"; tail -c 600 gpurun_out/${tag}_bench_final.json
+NCU="ncu --clock-control none"
+$NCU --metrics gpu__time_duration.sum -c 560 --csv --log-file gpurun_out/${tag}_launches_pangu.csv \
+    python bench.py --steps 3 --warmup 3 --only-headline --no-cpu-baseline > gpurun_out/ncu_lp.log 2>&1
+$NCU --metrics gpu__time_duration.sum -c 520 --csv --log-file gpurun_out/${tag}_launches_sfno.csv \
+    python bench.py --model sfno --steps 3 --warmup 3 --only-headline --no-cpu-baseline > gpurun_out/ncu_ls.log 2>&1
+$NCU --set full --import-source on -k regex:k_mlp_fused_pair --launch-skip 1 -c 2 -f -o gpurun_out/${tag}_mlp_full \
+    python tools/gpu_one_step.py 1 > gpurun_out/ncu_m.log 2>&1
+$NCU --set full --import-source on -k regex:k_window_attention_tc --launch-skip 1 -c 2 -f -o gpurun_out/${tag}_attn_full \
+    python tools/gpu_one_step.py 1 > gpurun_out/ncu_a.log 2>&1
+$NCU --set full --import-source on -k regex:k_gemm_pair -c 4 -f -o gpurun_out/${tag}_qkv_full \
+    python tools/gpu_one_step.py 1 > gpurun_out/ncu_q.log 2>&1
+$NCU --set full -k regex:k_gemm_batched --launch-skip 40 -c 12 -f -o gpurun_out/${tag}_sfno_gemm_full \
+    python tools/gpu_sfno.py full > gpurun_out/ncu_s.log 2>&1
+ls -la gpurun_out | tail -20
