@@ -5,19 +5,22 @@
 //
 // Every contraction of the step — per-pixel MLPs, the truncated longitude DFT, the Legendre
 // transforms (one GEMM per zonal wavenumber m), the per-degree complex channel mixing (one GEMM
-// per l) and their inverses — runs on the batched TMA-fed tcgen05 GEMM (gemm_batched.cuh) with
+// per l) and their inverses — runs on the batched TMA-fed tcgen05 GEMMs (gemm_batched.cuh, gemm_tb.cuh) with
 // 3-term fp16 splitting (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, ~22-bit mantissa: single-pass fp16
-// misses the 1e-3 budget on this network).  Between GEMMs, "pack" kernels
-// re-index an fp32 tensor into the hi / lo fp16 operand images of the next GEMM (applying the
-// instance-norm affine and GELU on the way).  Correctness-first structure: fp32 intermediates
-// live in HBM; fusing the packs into the producing epilogues is the obvious next step.
+// misses the 1e-3 budget on this network).
+// The spherical transforms are a chain of four "table x data" GEMMs around the mixing GEMM; the data is always the
+// MN-major B operand, read where the previous epilogue wrote it as fp16 hi / lo rows (no fp32 intermediates, no
+// transposing pack passes):
+//   pixel image [(lat,lon)][c] --DFT per lat--> [m][lat][(ri,c)] --Legendre per m--> [l][m][(ri,c)] --mixing per l-->
+//   [m][l][(ro,o)] --inverse Legendre per m--> [lat][(m,ro)][o] --inverse DFT per lat--> fp32 pixel-major [(lat,lon)][o]
+// "Pack" kernels remain where a normalisation needs global statistics first (instance norms) and for the state input.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "engine.h"
-#include "gemm_batched.cuh"
+#include "gemm_tb.cuh"
 
 namespace sky {
 
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(256) k_pack_tile(PackDesc d, int ext_d, int n_
 // ======================================================================================
 // weights / tables -> 3-term W images  [batch][N/BN][3*Kp/64][BN x 128 B]   ([hi | hi | lo] along K)
 //   mode 0: src[b*s_b + n*s_n + k*s_k]            (n < n_valid, k < k_valid)
-//   mode 1: complex channel mixing: src = W[l][o][i][2]; row n = (o, ro), col k = (i, ri):
+//   mode 1: complex channel mixing: src = W[l][o][i][2]; row n = (ro, o), col k = (ri, i)  (re/im-major: the spectra
+//           are stored as [.., (ri, c)] so that 64 consecutive channels share a 128-byte row):
 //           (ro,ri)=(0,0) Wr, (0,1) -Wi, (1,0) Wi, (1,1) Wr
 // ======================================================================================
 struct WPackDesc {
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
       if (d.mode == 0) {
         v = d.src[(long long)b * d.s_b + (long long)n * d.s_n + (long long)k * d.s_k];
       } else {
-        const int o = n >> 1, ro = n & 1, i = k >> 1, ri = k & 1;
+        const int ro = n / d.E, o = n - ro * d.E, ri = k / d.E, i = k - ri * d.E;
         const float* w = d.src + (((long long)b * d.E + o) * d.E + i) * 2;
         v = ro == ri ? w[0] : (ro == 1 ? w[1] : -w[1]);
       }
@@ -315,7 +319,10 @@ struct SfnoEngine : Engine {
   long long P1, P2;
   std::vector<void*> owned;
   // weights
-  W3 enc1, enc2, dec1, dec2, dftf_big, dftf_int, dfti_big, dfti_int, legf_big, legf_int, legi_big, legi_int;
+  W3 enc1, enc2, dec1, dec2;
+  // transform tables as A operands (128-row tiles): forward DFT [(m,ri)][lon], forward Legendre [m][l][lat],
+  // inverse Legendre [m][lat][l], inverse DFT [lon][(m,ri)]
+  W3 tdf_big, tdf_int, tdi_big, tdi_int, tpf_big, tpf_int, tpi_big, tpi_int;
   struct Blk { W3 spec, inner, fc1, fc2; const float *n0g, *n0b, *n1g, *n1b, *inner_b, *fc1_b, *fc2_b; };
   std::vector<Blk> blk;
   const float *mean, *stdv, *enc1_b, *enc2_b, *dec1_b, *dec2_b;
@@ -323,8 +330,10 @@ struct SfnoEngine : Engine {
   float *in_sc, *in_sh, *n_sc, *n_sh;
   double* sums;
   // scratch (engine owned, one member at a time)
-  float *X, *Xn, *F1, *Fd, *Fl, *Fs, *G, *Rpm;
-  Img2 I_a, I_b, I_cm, I_in, I_leg, I_spec, I_ileg, I_idft;
+  float *X, *Xn, *F1, *Rpm;
+  Img2 I_a, I_b, I_in;
+  // spectral-chain data images: LI [m][lat][(ri,c)], SI [l][m][(ri,c)], MI / MI2 [m][l][(ro,o)], DI [lat][(m,ro)][o]
+  Img2 LI, SI, MI, MI2, DI;
   bool scratch_ready = false;
 
   SfnoEngine(const sky_sfno_config_t& c, int dev) : cfg(c) {
@@ -356,7 +365,6 @@ struct SfnoEngine : Engine {
 
   // BLOCK_N policies (must match the template dispatch in gemm())
   int bn_point(int N) const { return N % 192 == 0 ? 192 : 64; }
-  int bn_dftf() const { return 2 * mmax <= 64 ? 64 : 256; }
   int bn_small(int N) const { return N >= 240 && N % 240 == 0 ? 240 : (N % 192 == 0 ? 192 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 16))); }
 
   int pack_w(W3& w, const float* src, int mode, int n_valid, int k_valid, int N, int BN, int batches, long long s_b,
@@ -395,24 +403,26 @@ struct SfnoEngine : Engine {
     if (dec1.Kp != E + CinP) { set_error("internal: decoder K padding"); return SKY_ERR_STATE; }
     const int NoutP = pad_to(Cin, 16);
     if ((rc = pack_w(dec2, w_d2, 0, Cin, E, NoutP, NoutP, 1, 0, E, 1, st))) return rc;
-    // DFT matrices  fwd [(m,ri)][lon],  inv [lon][(m,ri)]
-    P(t, "dft.fwd_big", 2LL * mmax * W1);
-    if ((rc = pack_w(dftf_big, t, 0, 2 * mmax, W1, pad_to(2 * mmax, bn_dftf()), bn_dftf(), 1, 0, W1, 1, st))) return rc;
-    P(t, "dft.fwd_int", 2LL * mmax * W2);
-    if ((rc = pack_w(dftf_int, t, 0, 2 * mmax, W2, pad_to(2 * mmax, bn_dftf()), bn_dftf(), 1, 0, W2, 1, st))) return rc;
-    P(t, "dft.inv_big", 2LL * mmax * W1);
-    if ((rc = pack_w(dfti_big, t, 0, W1, 2 * mmax, W1, bn_small(W1), 1, 0, 2 * mmax, 1, st))) return rc;
-    P(t, "dft.inv_int", 2LL * mmax * W2);
-    if ((rc = pack_w(dfti_int, t, 0, W2, 2 * mmax, W2, bn_small(W2), 1, 0, 2 * mmax, 1, st))) return rc;
-    // Legendre tables  fwd [m][l][k] -> W rows l, K = k ;  inv [m][k][l] -> W rows k, K = l
-    P(t, "sht.fwd_big", (long long)mmax * lmax * H1);
-    if ((rc = pack_w(legf_big, t, 0, lmax, H1, lmax, bn_small(lmax), mmax, (long long)lmax * H1, H1, 1, st))) return rc;
-    P(t, "sht.fwd_int", (long long)mmax * lmax * H2);
-    if ((rc = pack_w(legf_int, t, 0, lmax, H2, lmax, bn_small(lmax), mmax, (long long)lmax * H2, H2, 1, st))) return rc;
-    P(t, "sht.inv_big", (long long)mmax * lmax * H1);
-    { const int Np = pad_to(H1, 64); if ((rc = pack_w(legi_big, t, 0, H1, lmax, Np, bn_small(Np), mmax, (long long)lmax * H1, lmax, 1, st))) return rc; }
-    P(t, "sht.inv_int", (long long)mmax * lmax * H2);
-    if ((rc = pack_w(legi_int, t, 0, H2, lmax, H2, bn_small(H2), mmax, (long long)lmax * H2, lmax, 1, st))) return rc;
+    // transform tables as A operands (128-row tiles, [hi | hi | lo] along K)
+    {
+      const int r_dft = pad_to(2 * mmax, 128), r_l = pad_to(lmax, 128);
+      P(t, "dft.fwd_big", 2LL * mmax * W1);   // [(m,ri)][lon]
+      if ((rc = pack_w(tdf_big, t, 0, 2 * mmax, W1, r_dft, 128, 1, 0, W1, 1, st))) return rc;
+      P(t, "dft.fwd_int", 2LL * mmax * W2);
+      if ((rc = pack_w(tdf_int, t, 0, 2 * mmax, W2, r_dft, 128, 1, 0, W2, 1, st))) return rc;
+      P(t, "dft.inv_big", 2LL * mmax * W1);   // [lon][(m,ri)]
+      if ((rc = pack_w(tdi_big, t, 0, W1, 2 * mmax, pad_to(W1, 128), 128, 1, 0, 2 * mmax, 1, st))) return rc;
+      P(t, "dft.inv_int", 2LL * mmax * W2);
+      if ((rc = pack_w(tdi_int, t, 0, W2, 2 * mmax, pad_to(W2, 128), 128, 1, 0, 2 * mmax, 1, st))) return rc;
+      P(t, "sht.fwd_big", (long long)mmax * lmax * H1);   // [m][l][lat]
+      if ((rc = pack_w(tpf_big, t, 0, lmax, H1, r_l, 128, mmax, (long long)lmax * H1, H1, 1, st))) return rc;
+      P(t, "sht.fwd_int", (long long)mmax * lmax * H2);
+      if ((rc = pack_w(tpf_int, t, 0, lmax, H2, r_l, 128, mmax, (long long)lmax * H2, H2, 1, st))) return rc;
+      P(t, "sht.inv_big", (long long)mmax * lmax * H1);   // [m][lat][l]
+      if ((rc = pack_w(tpi_big, t, 0, H1, lmax, pad_to(H1, 128), 128, mmax, (long long)lmax * H1, lmax, 1, st))) return rc;
+      P(t, "sht.inv_int", (long long)mmax * lmax * H2);
+      if ((rc = pack_w(tpi_int, t, 0, H2, lmax, pad_to(H2, 128), 128, mmax, (long long)lmax * H2, lmax, 1, st))) return rc;
+    }
     blk.resize(L);
     for (int i = 0; i < L; ++i) {
       Blk& b = blk[i];
@@ -454,24 +464,20 @@ struct SfnoEngine : Engine {
     k_input_affine<<<1, 128, 0, st>>>(mean, stdv, Cin, in_sc, in_sh);
     count_launch();
     // ---- scratch ----
-    const int latp1 = pad_to(H1, 64);
     const size_t Hd = (size_t)cfg.mlp_ratio * E;
     X = dalloc<float>((size_t)P1 * E); Xn = dalloc<float>((size_t)P1 * E);
-    F1 = dalloc<float>((size_t)P1 * Hd);  // the last block's MLP runs on the full-resolution grid
+    F1 = dalloc<float>((size_t)P1 * E);
     Rpm = dalloc<float>((size_t)P1 * E);
-    Fd = dalloc<float>((size_t)E * H1 * dftf_big.N);
-    Fl = dalloc<float>((size_t)mmax * 2 * E * lmax);
-    Fs = dalloc<float>((size_t)lmax * pad_to(mmax, 128) * 2 * E);
-    G = dalloc<float>((size_t)mmax * 2 * E * latp1);
-    if (!X || !Xn || !F1 || !Rpm || !Fd || !Fl || !Fs || !G) return SKY_ERR_NOMEM;
-    const size_t ab = img_bytes(P1, (int)Hd);
+    if (!X || !Xn || !F1 || !Rpm) return SKY_ERR_NOMEM;
+    // one spare row tile: the last latitude's final k-block of the per-latitude DFT reads (and multiplies by the table's
+    // zero padding) up to 63 rows past the grid
+    const size_t ab = img_bytes(P1 + 128, (int)Hd);
     if (!img_alloc(I_a, ab) || !img_alloc(I_b, ab)) return SKY_ERR_NOMEM;
     if (!img_alloc(I_in, img_bytes(P1, Cin))) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_cm, img_bytes((long long)E * H1, W1))) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_leg, img_bytes(2 * E, H1, mmax))) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_spec, img_bytes(mmax, 2 * E, lmax))) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_ileg, img_bytes(2 * E, lmax, mmax))) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_idft, img_bytes((long long)H1 * E, 2 * mmax))) return SKY_ERR_NOMEM;
+    if (!img_alloc(LI, img_bytes(H1, 2 * E, mmax))) return SKY_ERR_NOMEM;
+    if (!img_alloc(SI, img_bytes(mmax, 2 * E, lmax))) return SKY_ERR_NOMEM;
+    if (!img_alloc(MI, img_bytes(lmax, 2 * E, mmax)) || !img_alloc(MI2, img_bytes(lmax, 2 * E, mmax))) return SKY_ERR_NOMEM;
+    if (!img_alloc(DI, img_bytes(2 * mmax, E, H1))) return SKY_ERR_NOMEM;
     SKY_CUDA_OK(cudaGetLastError());
     SKY_CUDA_OK(cudaStreamSynchronize(st));
     scratch_ready = true;
@@ -586,29 +592,66 @@ struct SfnoEngine : Engine {
     return 0;
   }
 
-  // inverse SHT of coefficient tensor `coef` (indexed [m][n=(c,ri)][l] when from_legendre, or
-  // [l][m][n] when from the spectral mixing) onto grid (Ho, Wo) -> pixel-major fp32 [Ho*Wo, E]
-  int inverse_sht(const float* coef, bool from_legendre, int Ho, int Wo, float* out_pm, const float* chan_bias, cudaStream_t st) {
-    const int n2 = 2 * E, lp = pad_to(lmax, 64);
-    const bool big = Ho == H1;
-    const W3& wl = big ? legi_big : legi_int;
-    const W3& wd = big ? dfti_big : dfti_int;
+  // ---- spherical transforms: table x data GEMMs (gemm_tb.cuh) ----
+  template <class Epi>
+  int gemm_tb(int tag, const W3& T, const BData& B, const Epi& epi, long long M, int N, int batches, cudaStream_t st) {
     int rc;
-    // A operand of the inverse Legendre GEMM: per m, rows n, cols l
-    if (from_legendre) rc = pack(KT_SFNO_ISHT, coef, I_ileg, mmax, 1, n2, lmax, (long long)n2 * lmax, 0, lmax, 2, 1, 0, nullptr, nullptr, 0, 0, 1, 2, 3, st);
-    else rc = pack(KT_SFNO_ISHT, coef, I_ileg, mmax, 1, n2, lmax, n2, 0, 1, 2LL * pad_to(mmax, 128) * n2, (long long)pad_to(mmax, 128) * n2, 0, nullptr, nullptr, 0, 1, 0, 2, 3, st);
-    if (rc) return rc;
-    // G[m][n][lat_pad] = A_m * Pinv_m^T
-    const long long a_bs = (long long)(pad_to(n2, 128) / 128) * (lp / 64) * G2_A_BYTES;
-    if ((rc = gemm(KT_SFNO_ISHT, I_ileg, lmax, a_bs, n2, G, wl.N, (long long)n2 * wl.N, nullptr, false, wl, n2, st))) return rc;
-    // A operand of the inverse DFT: rows (lat, c), cols (m, ri):  G[m][(c,ri)][lat]
-    if ((rc = pack(KT_SFNO_ISHT, G, I_idft, 1, Ho, E, 2 * mmax, 0, 1, 2LL * wl.N, (long long)n2 * wl.N, wl.N, 0, nullptr, nullptr, 0, 2, 1, 0, 3, st))) return rc;
-    // inverse longitude DFT, stored pixel-major [(lat, lon)][c] by the epilogue (no Fx buffer, no transpose pass)
-    if (E % 32) { set_error("internal: inverse_sht needs E %% 32 == 0"); return SKY_ERR_STATE; }
+    prof_begin(tag, st);
+    count_launch();
+    const long long tbs = T.batches > 1 ? T.batch_stride : 0;
+    const int bn = N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 64));
+#define SKY_TB(v) case v: rc = launch_gemm_tb<Epi, v, 8>(T.img, tbs, T.N, T.Kp, B, epi, M, N, batches, num_sms, st); break;
+    switch (bn) { SKY_TB(64) SKY_TB(128) SKY_TB(192) default: rc = launch_gemm_tb<Epi, 256, 8>(T.img, tbs, T.N, T.Kp, B, epi, M, N, batches, num_sms, st); }
+#undef SKY_TB
+    prof_end(tag, st);
+    return rc;
+  }
+  static long long tile_img_bytes(int rows, int K) { return (long long)(pad_to(rows, 128) / 128) * (pad_to(K, 64) / 64) * G2_A_BYTES; }
+
+  // forward SHT of the pixel image D (normalised block input on grid (Hi, Wi)):
+  //   per latitude  F[(m,ri)][c] = Tf[(m,ri)][lon] * D[lon][c]            -> LI[m][lat][(ri,c)]
+  //   per m         S[l][(ri,c)] = Pf_m[l][lat]  * LI_m[lat][(ri,c)]      -> `to_mixing` as [l][m][(ri,c)] (A images of the
+  //                 mixing GEMM) and / or `to_inverse` as [m][l][(ri,c)] (data of an inverse transform: the residual of a
+  //                 grid-changing block); the second layout costs a second pass of the (cheap) Legendre GEMM
+  int forward_sht(const Img2& D, int Hi, int Wi, Img2* to_mixing, Img2* to_inverse, cudaStream_t st) {
+    const bool big = Hi == H1;
+    const int n2 = 2 * E;
+    int rc;
+    const long long li_b = tile_img_bytes(Hi, n2);
     {
-      EpiF32PixelMajor e{out_pm, E, Wo, Wo, chan_bias};
-      const int nkb = pad_to(2 * mmax, 64) / 64, mt = pad_to((int)((long long)Ho * E), 128) / 128;
-      if ((rc = gemm_epi(KT_SFNO_ISHT, I_idft, nkb, 0, mt, e, wd, (long long)Ho * E, st))) return rc;
+      BData bd{D.hi, D.lo, E / 64, Wi, 0};
+      EpiSplitRemap e{LI.hi, LI.lo, li_b, n2 / 64, 2, E, 1 << 30, 1, E};
+      if ((rc = gemm_tb(KT_SFNO_SHT, big ? tdf_big : tdf_int, bd, e, 2 * mmax, E, Hi, st))) return rc;
+    }
+    BData bd{LI.hi, LI.lo, n2 / 64, 0, li_b};
+    if (to_mixing) {   // batch' = l (source row), row' = m (source batch)
+      EpiSplitRemap e{to_mixing->hi, to_mixing->lo, tile_img_bytes(mmax, n2), n2 / 64, 1, 0, 1 << 30, 1, n2};
+      if ((rc = gemm_tb(KT_SFNO_SHT, big ? tpf_big : tpf_int, bd, e, lmax, n2, mmax, st))) return rc;
+    }
+    if (to_inverse) {
+      EpiSplitRemap e{to_inverse->hi, to_inverse->lo, tile_img_bytes(lmax, n2), n2 / 64, 1, 0, 1 << 30, 1, n2, 1};
+      if ((rc = gemm_tb(KT_SFNO_SHT, big ? tpf_big : tpf_int, bd, e, lmax, n2, mmax, st))) return rc;
+    }
+    return 0;
+  }
+
+  // inverse SHT of the spectrum image S ([m][l][(ro,o)]) onto grid (Ho, Wo) -> fp32 pixel-major [Ho*Wo, E] (+ per-channel bias)
+  //   per m         G[lat][(ro,o)] = Pi_m[lat][l] * S_m[l][(ro,o)]          -> DI[lat][(m,ro)][o]
+  //   per latitude  y[lon][o]      = Ti[lon][(m,ro)] * DI_lat[(m,ro)][o]    -> out_pm[(lat*Wo + lon)*E + o]
+  int inverse_sht(const Img2& S, int Ho, int Wo, float* out_pm, const float* chan_bias, cudaStream_t st) {
+    const bool big = Ho == H1;
+    const int n2 = 2 * E;
+    int rc;
+    const long long di_b = tile_img_bytes(2 * mmax, E);
+    {
+      BData bd{S.hi, S.lo, n2 / 64, 0, tile_img_bytes(lmax, n2)};
+      EpiSplitRemap e{DI.hi, DI.lo, di_b, E / 64, 1, 0, E, 2, n2};
+      if ((rc = gemm_tb(KT_SFNO_ISHT, big ? tpi_big : tpi_int, bd, e, Ho, n2, mmax, st))) return rc;
+    }
+    {
+      BData bd{DI.hi, DI.lo, E / 64, 0, di_b};
+      EpiF32Batched<false> e{out_pm, E, (long long)Wo * E, chan_bias, E, nullptr};
+      if ((rc = gemm_tb(KT_SFNO_ISHT, big ? tdi_big : tdi_int, bd, e, Wo, E, Ho, st))) return rc;
     }
     return 0;
   }
@@ -622,33 +665,28 @@ struct SfnoEngine : Engine {
     int rc;
     // norm0 statistics of the block input
     if ((rc = norm_stats(xin, Pi, 0, b.n0g, b.n0b, st))) return rc;
-    // forward SHT of norm0(x):  channel-major rows (c, lat), cols lon
-    if ((rc = pack(KT_SFNO_SHT, xin, I_cm, 1, E, Hi, Wi, 0, 1, (long long)Wi * E, 2LL * E, E, 1, n_sc, n_sh, 0, 2, 0, 1, 3, st))) return rc;
-    const W3& wdf = in_big ? dftf_big : dftf_int;
-    if ((rc = gemm(KT_SFNO_SHT, I_cm, Wi, 0, (long long)E * Hi, Fd, wdf.N, 0, nullptr, false, wdf, (long long)E * Hi, st))) return rc;
-    // Legendre A operand per m: rows n = (c, ri), cols lat:  Fd[(c*Hi + lat)][2m + ri]
-    if ((rc = pack(KT_SFNO_SHT, Fd, I_leg, mmax, E, 2, Hi, 2, (long long)Hi * wdf.N, 1, 2LL * wdf.N, wdf.N, 0, nullptr, nullptr, 0, 1, 3, 2, 0, st))) return rc;
-    const W3& wlf = in_big ? legf_big : legf_int;
-    const long long leg_bs = (long long)(pad_to(n2, 128) / 128) * (pad_to(Hi, 64) / 64) * G2_A_BYTES;
-    if ((rc = gemm(KT_SFNO_SHT, I_leg, Hi, leg_bs, n2, Fl, lmax, (long long)n2 * lmax, nullptr, false, wlf, n2, st))) return rc;
-    // residual: norm0(x) on the output grid
+    // pixel image of norm0(x) (hi / lo, K = channels): the data of the forward DFT and the A operand of the inner skip;
+    // on an unchanged grid its fp32 copy is the residual of the outer skip
     if (Hi == Ho) {
       if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st, Rpm, E))) return rc;
+      if ((rc = forward_sht(I_a, Hi, Wi, &SI, nullptr, st))) return rc;
     } else {
+      if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st))) return rc;
+      if ((rc = forward_sht(I_a, Hi, Wi, &SI, &MI2, st))) return rc;
       // only the OUTER skip needs the resampled residual as a field; the inner skip lives in the mixing matrices
-      if ((rc = inverse_sht(Fl, true, Ho, Wo, Rpm, nullptr, st))) return rc;
+      if ((rc = inverse_sht(MI2, Ho, Wo, Rpm, nullptr, st))) return rc;
     }
-    // spectral channel mixing, one GEMM per degree l: rows m, K = (i, ri):  Fl[m][(i,ri)][l]
-    if ((rc = pack(KT_SFNO_SPEC, Fl, I_spec, lmax, 1, mmax, n2, 1, 0, (long long)n2 * lmax, 2LL * lmax, lmax, 0, nullptr, nullptr, 0, 3, 0, 1, 2, st))) return rc;
-    const int mp = pad_to(mmax, 128);
-    const long long spec_bs = (long long)(mp / 128) * (pad_to(n2, 64) / 64) * G2_A_BYTES;
-    if ((rc = gemm(KT_SFNO_SPEC, I_spec, n2, spec_bs, mmax, Fs, n2, (long long)mp * n2, nullptr, false, b.spec, mmax, st))) return rc;
+    // spectral channel mixing, one GEMM per degree l: rows m, K = (ri, i); written as the inverse Legendre's data [m][l][(ro,o)]
+    {
+      EpiSplitRemap e{MI.hi, MI.lo, tile_img_bytes(lmax, n2), n2 / 64, 1, 0, 1 << 30, 1, n2};
+      if ((rc = gemm_epi(KT_SFNO_SPEC, SI, n2 / 64, tile_img_bytes(mmax, n2), pad_to(mmax, 128) / 128, e, b.spec, mmax, st))) return rc;
+    }
     // y = iSHT(mixed) + inner_skip(residual) + bias  (pixel-major fp32 in F1)
     if (Hi == Ho) {
-      if ((rc = inverse_sht(Fs, false, Ho, Wo, F1, nullptr, st))) return rc;
+      if ((rc = inverse_sht(MI, Ho, Wo, F1, nullptr, st))) return rc;
       if ((rc = gemm(KT_SFNO_MLP, I_a, E, 0, Po, F1, E, 0, b.inner_b, true, b.inner, Po, st))) return rc;
     } else {
-      if ((rc = inverse_sht(Fs, false, Ho, Wo, F1, b.inner_b, st))) return rc;   // folded inner skip: only its bias is left
+      if ((rc = inverse_sht(MI, Ho, Wo, F1, b.inner_b, st))) return rc;   // folded inner skip: only its bias is left
     }
     // norm1(GELU(y)) -> MLP
     if ((rc = norm_stats(F1, Po, 1, b.n1g, b.n1b, st))) return rc;

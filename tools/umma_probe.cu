@@ -268,6 +268,24 @@ int main(int argc, char** argv) {
     c.row_hi = 32;
     bad += run(c);
   }
+  // 7. MN-major B wider than one 64-element swizzle atom (SFNO: data as the B operand, N = channels): atoms of
+  //    [64 k-rows][128 B] stacked along N, `blk` bytes apart.  Which descriptor field carries the atom stride?
+  for (int variant = 0; variant < 4; ++variant) {
+    const int N = variant < 2 ? 192 : 256;
+    const bool lbo_is_atom_stride = (variant & 1) == 0;
+    Case c; char* nm = new char[96];
+    snprintf(nm, 96, "B mn-major sw128 N%d, atom stride 8 KB in %s", N, lbo_is_atom_stride ? "LBO (SBO 1024)" : "SBO (LBO 1024)");
+    c.name = nm;
+    fill(c, 128, N, 64);
+    for (int m = 0; m < 128; ++m) for (int k = 0; k < 64; ++k) put16(c.a_img, kmaj(m, k, 128), c.A[m * 64 + k]);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < 64; ++k) put16(c.b_img, (size_t)(n / 64) * 8192 + mnmaj(k, n % 64), c.B[(size_t)n * 64 + k]);
+    c.args = ProbeArgs{};
+    c.args.desc_a_hi = desc_hi(16, 1024, 2);
+    c.args.desc_b_hi = lbo_is_atom_stride ? desc_hi(8192, 1024, 2) : desc_hi(1024, 8192, 2);
+    c.args.a_inc = 32; c.args.b_inc = 16 * 128;
+    c.args.idesc = idesc_f16(128, N, 0, 1); c.args.ksteps = 4;
+    bad += run(c);
+  }
   printf("probe finished: %d mismatching case(s)\n", bad);
   return 0;
 }
