@@ -231,4 +231,89 @@ struct EpiSplitRemap {
   }
 };
 
+// y = acc (+ bias[col]) (+ addend[pixel][col]);  g = GELU(y)  ->  hi / lo fp16 rows of the pixel image of g (the next
+// pointwise GEMM's A operand) AND per-channel sum / sum of squares of g (instance-norm statistics of the following norm,
+// whose affine is folded into that GEMM's weights once the statistics are final).  Replaces: fp32 store of y, a
+// statistics pass over it, and the GELU + normalise + split pack pass.  Pixel row = batch * rows_per_batch + row.
+struct EpiGeluStatsImg {
+  static constexpr bool kNeedsBias = false;
+  uint8_t* hi; uint8_t* lo; int nkb;
+  const float* bias;          // per column, may be null
+  const float* add; int ld;   // fp32 addend [pixel][ld], may be null
+  long long rows_per_batch;
+  double* sums;               // [n_valid] sums, then [n_valid] sums of squares
+  int n_valid;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtxB& x) const {
+    const int rsub = x.lane >> 2, ch = x.lane & 3;
+    const long long p0 = (long long)x.batch * rows_per_batch + x.row0;   // pixel row of this warp's first accumulator row
+    for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
+      const int col = x.n0 + c + ch * 8;
+      const bool cols_ok = c + ch * 8 < BN && col < n_valid;
+      float4 a0[4], a1[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {   // all global reads of the chunk first (see EpiF32Batched)
+        const int rr = it * 8 + rsub;
+        a0[it] = a1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add && cols_ok && x.row0 + rr < x.M) {
+          const float* ap = add + (size_t)(p0 + rr) * ld + col;
+          a0[it] = __ldg(reinterpret_cast<const float4*>(ap));
+          a1[it] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+        }
+      }
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (bias && cols_ok) { b0 = __ldg(reinterpret_cast<const float4*>(bias + col)); b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4)); }
+      {
+        float v[32];
+        acc.load32(c, v);
+        patch_put_v(x.patch_s, x.lane, v);
+      }
+      __syncwarp();
+      float s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + rsub;
+        const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+        const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+        float f[8] = {t0.x + a0[it].x, t0.y + a0[it].y, t0.z + a0[it].z, t0.w + a0[it].w,
+                      t1.x + a1[it].x, t1.y + a1[it].y, t1.z + a1[it].z, t1.w + a1[it].w};
+        gelu_erf_x2(f[0], f[1], b0.x, b0.y); gelu_erf_x2(f[2], f[3], b0.z, b0.w);
+        gelu_erf_x2(f[4], f[5], b1.x, b1.y); gelu_erf_x2(f[6], f[7], b1.z, b1.w);
+        if (cols_ok && x.row0 + rr < x.M) {
+          __half h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            h[e] = __float2half_rn(f[e]); l[e] = __float2half_rn(f[e] - __half2float(h[e]));
+            s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]);
+          }
+          const long long p = p0 + rr;
+          const size_t o = ((size_t)(p >> 7) * nkb + (size_t)(col >> 6)) * G2_A_BYTES + sw128_offset((uint32_t)(p & 127), (col & 63) >> 3);
+          *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+      // the 8 lanes that share a column group (same lane & 3) hold 4 rows each: butterfly over lane bits 2..4, then one
+      // fp64 atomic per column and statistic from the lanes with rsub == 0
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int d = 4; d < 32; d <<= 1) {
+          s[e] += __shfl_xor_sync(0xffffffffu, s[e], d);
+          q[e] += __shfl_xor_sync(0xffffffffu, q[e], d);
+        }
+      }
+      if (rsub == 0 && cols_ok) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(sums + col + e, (double)s[e]);
+          atomicAdd(sums + n_valid + col + e, (double)q[e]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
 }  // namespace sky

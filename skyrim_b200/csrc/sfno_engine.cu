@@ -163,6 +163,7 @@ struct WPackDesc {
   const float* src; long long s_b, s_n, s_k;
   int n_valid, k_valid, N, Kp, BN, batches, mode, E;
   uint8_t* img;
+  const float* kscale;   // optional per-k factor (an instance-norm scale folded into the weights), mode 0
 };
 __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
     if (n < d.n_valid && k < d.k_valid) {
       if (d.mode == 0) {
         v = d.src[(long long)b * d.s_b + (long long)n * d.s_n + (long long)k * d.s_k];
+        if (d.kscale) v *= d.kscale[k];
       } else {
         const int ro = n / d.E, o = n - ro * d.E, ri = k / d.E, i = k - ri * d.E;
         const float* w = d.src + (((long long)b * d.E + o) * d.E + i) * 2;
@@ -254,6 +256,17 @@ __global__ void k_finalize_norm(const double* __restrict__ sums, const float* __
   sc[c] = s;
   sh[c] = b[c] - (float)mean * s;
 }
+// bias'[n] = bias[n] + sum_k W[n][k] * shift[k]   (the shift of a folded instance norm); one warp per output
+__global__ void k_fold_bias(const float* __restrict__ W, const float* __restrict__ shift, const float* __restrict__ bias,
+                            float* __restrict__ out, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (n >= N) return;
+  float a = 0.f;
+  for (int k = lane; k < K; k += 32) a = fmaf(W[(size_t)n * K + k], shift[k], a);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  if (lane == 0) out[n] = bias[n] + a;
+}
 __global__ void k_input_affine(const float* __restrict__ mean, const float* __restrict__ stdv, int C,
                                float* __restrict__ sc, float* __restrict__ sh) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +336,8 @@ struct SfnoEngine : Engine {
   // transform tables as A operands (128-row tiles): forward DFT [(m,ri)][lon], forward Legendre [m][l][lat],
   // inverse Legendre [m][lat][l], inverse DFT [lon][(m,ri)]
   W3 tdf_big, tdf_int, tdi_big, tdi_int, tpf_big, tpf_int, tpi_big, tpi_int;
-  struct Blk { W3 spec, inner, fc1, fc2; const float *n0g, *n0b, *n1g, *n1b, *inner_b, *fc1_b, *fc2_b; };
+  struct Blk { W3 spec, inner, fc1, fc2; const float *n0g, *n0b, *n1g, *n1b, *inner_b, *fc1_b, *fc2_b, *fc1_w; };
+  float* fc1_bs = nullptr;   // fc1 bias with norm1's shift folded in (rewritten per block and step)
   std::vector<Blk> blk;
   const float *mean, *stdv, *enc1_b, *enc2_b, *dec1_b, *dec2_b;
   float* pos_pm = nullptr;  // [P1, E]
@@ -374,9 +388,23 @@ struct SfnoEngine : Engine {
     w.batch_stride = (long long)N * 3 * w.Kp * 2;
     w.img = dalloc<uint8_t>((size_t)w.batch_stride * batches);
     if (!w.img) return SKY_ERR_NOMEM;
-    WPackDesc d{src, s_b, s_n, s_k, n_valid, k_valid, N, w.Kp, BN, batches, mode, E, w.img};
-    const long long total = (long long)batches * N * (w.Kp / 8);
+    return fill_w(w, src, mode, n_valid, k_valid, s_b, s_n, s_k, nullptr, st);
+  }
+  // (re)write the image of an allocated W3; kscale: per-k factor folded into the weights (per step, after the statistics)
+  int fill_w(const W3& w, const float* src, int mode, int n_valid, int k_valid, long long s_b, long long s_n, long long s_k,
+             const float* kscale, cudaStream_t st) {
+    WPackDesc d{src, s_b, s_n, s_k, n_valid, k_valid, w.N, w.Kp, w.BN, w.batches, mode, E, w.img, kscale};
+    const long long total = (long long)w.batches * w.N * (w.Kp / 8);
     k_pack_w3<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, total);
+    count_launch();
+    SKY_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  // instance norm folded into the pointwise GEMM that follows it:  W (sc * g + sh) + b = (W diag(sc)) g + (W sh + b)
+  int fold_norm(const W3& dst, float* bias_out, const float* Wsrc, const float* bias, int N, int K, cudaStream_t st) {
+    int rc;
+    if ((rc = fill_w(dst, Wsrc, 0, N, K, 0, K, 1, n_sc, st))) return rc;
+    k_fold_bias<<<(N * 32 + 255) / 256, 256, 0, st>>>(Wsrc, n_sh, bias, bias_out, N, K);
     count_launch();
     SKY_CUDA_OK(cudaGetLastError());
     return 0;
@@ -443,8 +471,9 @@ struct SfnoEngine : Engine {
       }
       if ((rc = pack_w(b.spec, w, 1, 2 * E, 2 * E, 2 * E, bn_point(2 * E), lmax, 0, 0, 0, st))) return rc;
       const int Hd = cfg.mlp_ratio * E;
-      P(w, N("fc1.w"), (long long)Hd * E); KEEP(b.fc1_b, N("fc1.b"), Hd);
-      if ((rc = pack_w(b.fc1, w, 0, Hd, E, Hd, bn_point(Hd), 1, 0, E, 1, st))) return rc;
+      // fc1 is re-packed every step with norm1's scale folded in (fold_norm): keep the fp32 weights
+      KEEP(b.fc1_w, N("fc1.w"), (long long)Hd * E); KEEP(b.fc1_b, N("fc1.b"), Hd);
+      if ((rc = pack_w(b.fc1, b.fc1_w, 0, Hd, E, Hd, bn_point(Hd), 1, 0, E, 1, st))) return rc;
       P(w, N("fc2.w"), (long long)E * Hd); KEEP(b.fc2_b, N("fc2.b"), E);
       if ((rc = pack_w(b.fc2, w, 0, E, Hd, E, bn_point(E), 1, 0, Hd, 1, st))) return rc;
     }
@@ -460,7 +489,8 @@ struct SfnoEngine : Engine {
     }
     in_sc = dalloc<float>(512); in_sh = dalloc<float>(512); n_sc = dalloc<float>(E); n_sh = dalloc<float>(E);
     sums = dalloc<double>(2 * E);
-    if (!in_sc || !in_sh || !n_sc || !n_sh || !sums) return SKY_ERR_NOMEM;
+    fc1_bs = dalloc<float>((size_t)cfg.mlp_ratio * E);
+    if (!in_sc || !in_sh || !n_sc || !n_sh || !sums || !fc1_bs) return SKY_ERR_NOMEM;
     k_input_affine<<<1, 128, 0, st>>>(mean, stdv, Cin, in_sc, in_sh);
     count_launch();
     // ---- scratch ----
@@ -635,10 +665,12 @@ struct SfnoEngine : Engine {
     return 0;
   }
 
-  // inverse SHT of the spectrum image S ([m][l][(ro,o)]) onto grid (Ho, Wo) -> fp32 pixel-major [Ho*Wo, E] (+ per-channel bias)
+  // inverse SHT of the spectrum image S ([m][l][(ro,o)]) onto grid (Ho, Wo); `e_out` is the epilogue of the last GEMM
+  // (batch = latitude, row = longitude, column = channel: fp32 pixel-major store, or GELU + statistics + pixel image)
   //   per m         G[lat][(ro,o)] = Pi_m[lat][l] * S_m[l][(ro,o)]          -> DI[lat][(m,ro)][o]
-  //   per latitude  y[lon][o]      = Ti[lon][(m,ro)] * DI_lat[(m,ro)][o]    -> out_pm[(lat*Wo + lon)*E + o]
-  int inverse_sht(const Img2& S, int Ho, int Wo, float* out_pm, const float* chan_bias, cudaStream_t st) {
+  //   per latitude  y[lon][o]      = Ti[lon][(m,ro)] * DI_lat[(m,ro)][o]    -> e_out
+  template <class EpiOut>
+  int inverse_sht(const Img2& S, int Ho, int Wo, const EpiOut& e_out, cudaStream_t st) {
     const bool big = Ho == H1;
     const int n2 = 2 * E;
     int rc;
@@ -648,13 +680,10 @@ struct SfnoEngine : Engine {
       EpiSplitRemap e{DI.hi, DI.lo, di_b, E / 64, 1, 0, E, 2, n2};
       if ((rc = gemm_tb(KT_SFNO_ISHT, big ? tpi_big : tpi_int, bd, e, Ho, n2, mmax, st))) return rc;
     }
-    {
-      BData bd{DI.hi, DI.lo, E / 64, 0, di_b};
-      EpiF32Batched<false> e{out_pm, E, (long long)Wo * E, chan_bias, E, nullptr};
-      if ((rc = gemm_tb(KT_SFNO_ISHT, big ? tdi_big : tdi_int, bd, e, Wo, E, Ho, st))) return rc;
-    }
-    return 0;
+    BData bd{DI.hi, DI.lo, E / 64, 0, di_b};
+    return gemm_tb(KT_SFNO_ISHT, big ? tdi_big : tdi_int, bd, e_out, Wo, E, Ho, st);
   }
+  EpiF32Batched<false> to_field(float* out_pm, int Wo) const { return EpiF32Batched<false>{out_pm, E, (long long)Wo * E, nullptr, E, nullptr}; }
 
   int run_block(int i, float*& xin, float*& xout, cudaStream_t st) {
     const Blk& b = blk[i];
@@ -674,25 +703,32 @@ struct SfnoEngine : Engine {
       if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st))) return rc;
       if ((rc = forward_sht(I_a, Hi, Wi, &SI, &MI2, st))) return rc;
       // only the OUTER skip needs the resampled residual as a field; the inner skip lives in the mixing matrices
-      if ((rc = inverse_sht(MI2, Ho, Wo, Rpm, nullptr, st))) return rc;
+      if ((rc = inverse_sht(MI2, Ho, Wo, to_field(Rpm, Wo), st))) return rc;
     }
     // spectral channel mixing, one GEMM per degree l: rows m, K = (ri, i); written as the inverse Legendre's data [m][l][(ro,o)]
     {
       EpiSplitRemap e{MI.hi, MI.lo, tile_img_bytes(lmax, n2), n2 / 64, 1, 0, 1 << 30, 1, n2};
       if ((rc = gemm_epi(KT_SFNO_SPEC, SI, n2 / 64, tile_img_bytes(mmax, n2), pad_to(mmax, 128) / 128, e, b.spec, mmax, st))) return rc;
     }
-    // y = iSHT(mixed) + inner_skip(residual) + bias  (pixel-major fp32 in F1)
+    // g = GELU(iSHT(mixed) + inner_skip(residual) + bias) -> pixel image I_b + norm1 statistics, from the epilogue that
+    // produces y (the inner-skip GEMM on an unchanged grid, the inverse DFT when the inner skip is folded)
+    SKY_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * E * sizeof(double), st));
     if (Hi == Ho) {
-      if ((rc = inverse_sht(MI, Ho, Wo, F1, nullptr, st))) return rc;
-      if ((rc = gemm(KT_SFNO_MLP, I_a, E, 0, Po, F1, E, 0, b.inner_b, true, b.inner, Po, st))) return rc;
+      if ((rc = inverse_sht(MI, Ho, Wo, to_field(F1, Wo), st))) return rc;
+      EpiGeluStatsImg e{I_b.hi, I_b.lo, E / 64, b.inner_b, F1, E, 0, sums, E};
+      if ((rc = gemm_epi(KT_SFNO_MLP, I_a, E / 64, 0, 0, e, b.inner, Po, st))) return rc;
     } else {
-      if ((rc = inverse_sht(MI, Ho, Wo, F1, b.inner_b, st))) return rc;   // folded inner skip: only its bias is left
+      EpiGeluStatsImg e{I_b.hi, I_b.lo, E / 64, b.inner_b, nullptr, E, Wo, sums, E};
+      if ((rc = inverse_sht(MI, Ho, Wo, e, st))) return rc;
     }
-    // norm1(GELU(y)) -> MLP
-    if ((rc = norm_stats(F1, Po, 1, b.n1g, b.n1b, st))) return rc;
-    if ((rc = pack(KT_SFNO_MLP, F1, I_b, 1, 1, (int)Po, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 1, 0, 1, 2, 3, st))) return rc;
+    // norm1 folded into fc1:  fc1(norm1(g)) = (W1 diag(sc)) g + (W1 sh + b1)
+    prof_begin(KT_SFNO_MISC, st);
+    k_finalize_norm<<<(E + 127) / 128, 128, 0, st>>>(sums, b.n1g, b.n1b, cfg.eps, Po, E, n_sc, n_sh);
+    count_launch();
+    if ((rc = fold_norm(b.fc1, fc1_bs, b.fc1_w, b.fc1_b, Hd, E, st))) return rc;
+    prof_end(KT_SFNO_MISC, st);
     // GELU(fc1) goes straight into the operand images of fc2 (I_a: the residual image it held was consumed by the inner skip)
-    if ((rc = gemm_to_img(KT_SFNO_MLP, I_b, E, Po, I_a, Hd, b.fc1_b, true, b.fc1, st))) return rc;
+    if ((rc = gemm_to_img(KT_SFNO_MLP, I_b, E, Po, I_a, Hd, fc1_bs, true, b.fc1, st))) return rc;
     // x_out = residual + fc2(...): the residual is an addend of the epilogue (no copy, no read-modify-write)
     if ((rc = gemm(KT_SFNO_MLP, I_a, Hd, 0, Po, xout, E, 0, b.fc2_b, false, b.fc2, Po, st, Rpm))) return rc;
     float* tmp = xin; xin = xout; xout = tmp;
