@@ -191,6 +191,9 @@ struct EpiSplitRemap {
   int bdiv, kmul, kdiv, rb;
   int n_valid;
   int same = 0;                // 1: no permutation (batch' = b, row' = r, k' = c): the same spectrum laid out for an inverse
+  // optional instance-norm affine of the DATA folded behind the (linear) transform:  T (sc x + sh 1) = sc (T x) + sh (T 1):
+  // per-column scale / shift and the table's row sums t1[r] (forward DFT: only the m = 0 real row is non-zero)
+  const float* csc = nullptr; const float* csh = nullptr; const float* t1 = nullptr;
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtxB& x) const {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
@@ -205,14 +208,28 @@ struct EpiSplitRemap {
       __syncwarp();
       if (cols_ok) {
         const int cq = col / kdiv, cr = col - cq * kdiv;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = 1.f; sh[e] = 0.f; }
+        if (csc) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(csc + col)), s1 = __ldg(reinterpret_cast<const float4*>(csc + col + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(csh + col)), h1 = __ldg(reinterpret_cast<const float4*>(csh + col + 4));
+          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+          sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+        }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rr = it * 8 + rsub;
           const long long r = x.row0 + rr;
           if (r < x.M) {
-            const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
-            const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
-            const float f[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            const float4 q0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+            const float4 q1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+            float f[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            if (csc) {
+              const float tr = __ldg(t1 + r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[e], sh[e] * tr);
+            }
             __half h[8], l[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { h[e] = __float2half_rn(f[e]); l[e] = __float2half_rn(f[e] - __half2float(h[e])); }
@@ -309,6 +326,105 @@ struct EpiGeluStatsImg {
         for (int e = 0; e < 8; ++e) {
           atomicAdd(sums + col + e, (double)s[e]);
           atomicAdd(sums + n_valid + col + e, (double)q[e]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
+// x_out = acc + bias[col] + addend, where addend = asc[col] * add[pixel][col] + ash[col] (the outer skip: norm0 of the block
+// input, evaluated on the fly) or plain add[pixel][col] (positional embedding, resampled residual).  Writes the fp32 state
+// (the next block's skip source), its hi / lo pixel image (the next block's transform data and inner-skip operand, or the
+// decoder's input) and per-channel sum / sum of squares (the next block's norm0) in one pass.
+struct EpiF32ImgStats {
+  static constexpr bool kNeedsBias = false;
+  float* out; int ld;          // out may be null when nothing reads the fp32 state (the image is always written)
+  uint8_t* hi; uint8_t* lo; int nkb;
+  const float* bias;
+  const float* add; const float* asc; const float* ash;   // add may be null; asc / ash null = plain addend
+  double* sums;                                           // may be null (last block: no norm follows)
+  int n_valid;
+  template <int BN, class Acc>
+  __device__ void run(Acc& acc, const EpiCtxB& x) const {
+    const int rsub = x.lane >> 2, ch = x.lane & 3;
+    for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
+      const int col = x.n0 + c + ch * 8;
+      const bool cols_ok = c + ch * 8 < BN && col < n_valid;
+      float4 a0[4], a1[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + rsub;
+        a0[it] = a1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add && cols_ok && x.row0 + rr < x.M) {
+          const float* ap = add + (size_t)(x.row0 + rr) * ld + col;
+          a0[it] = __ldg(reinterpret_cast<const float4*>(ap));
+          a1[it] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+        }
+      }
+      float bb[8], sc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { bb[e] = 0.f; sc[e] = 1.f; }
+      if (cols_ok) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+        if (asc) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(asc + col)), s1 = __ldg(reinterpret_cast<const float4*>(asc + col + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(ash + col)), h1 = __ldg(reinterpret_cast<const float4*>(ash + col + 4));
+          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+          bb[0] += h0.x; bb[1] += h0.y; bb[2] += h0.z; bb[3] += h0.w; bb[4] += h1.x; bb[5] += h1.y; bb[6] += h1.z; bb[7] += h1.w;
+        }
+      }
+      {
+        float v[32];
+        acc.load32(c, v);
+        patch_put_v(x.patch_s, x.lane, v);
+      }
+      __syncwarp();
+      float s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + rsub;
+        const long long p = x.row0 + rr;
+        if (cols_ok && p < x.M) {
+          const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+          const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+          const float av[8] = {a0[it].x, a0[it].y, a0[it].z, a0[it].w, a1[it].x, a1[it].y, a1[it].z, a1[it].w};
+          float f[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          __half h[8], l[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = f[e] + fmaf(av[e], sc[e], bb[e]);
+            h[e] = __float2half_rn(f[e]); l[e] = __float2half_rn(f[e] - __half2float(h[e]));
+            s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]);
+          }
+          if (out) {
+            float* op = out + (size_t)p * ld + col;
+            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          const size_t o = ((size_t)(p >> 7) * nkb + (size_t)(col >> 6)) * G2_A_BYTES + sw128_offset((uint32_t)(p & 127), (col & 63) >> 3);
+          *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+        }
+      }
+      if (sums) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+          for (int d = 4; d < 32; d <<= 1) {
+            s[e] += __shfl_xor_sync(0xffffffffu, s[e], d);
+            q[e] += __shfl_xor_sync(0xffffffffu, q[e], d);
+          }
+        }
+        if (rsub == 0 && cols_ok) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            atomicAdd(sums + col + e, (double)s[e]);
+            atomicAdd(sums + n_valid + col + e, (double)q[e]);
+          }
         }
       }
       __syncwarp();

@@ -267,6 +267,16 @@ __global__ void k_fold_bias(const float* __restrict__ W, const float* __restrict
   for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
   if (lane == 0) out[n] = bias[n] + a;
 }
+// t1[r] = sum_k T[r][k]  (row sums of a transform table: what the transform makes of a constant field)
+__global__ void k_row_sums(const float* __restrict__ T, int rows, int K, float* __restrict__ out) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (r >= rows) return;
+  float a = 0.f;
+  for (int k = lane; k < K; k += 32) a += T[(size_t)r * K + k];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  if (lane == 0) out[r] = a;
+}
 __global__ void k_input_affine(const float* __restrict__ mean, const float* __restrict__ stdv, int C,
                                float* __restrict__ sc, float* __restrict__ sh) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,8 +346,11 @@ struct SfnoEngine : Engine {
   // transform tables as A operands (128-row tiles): forward DFT [(m,ri)][lon], forward Legendre [m][l][lat],
   // inverse Legendre [m][lat][l], inverse DFT [lon][(m,ri)]
   W3 tdf_big, tdf_int, tdi_big, tdi_int, tpf_big, tpf_int, tpi_big, tpi_int;
-  struct Blk { W3 spec, inner, fc1, fc2; const float *n0g, *n0b, *n1g, *n1b, *inner_b, *fc1_b, *fc2_b, *fc1_w; };
-  float* fc1_bs = nullptr;   // fc1 bias with norm1's shift folded in (rewritten per block and step)
+  struct Blk { W3 spec, inner, fc1, fc2; const float *n0g, *n0b, *n1g, *n1b, *inner_b, *fc1_b, *fc2_b, *fc1_w, *inner_w; };
+  float *fc1_bs = nullptr, *inner_bs = nullptr;   // biases with a folded norm's shift (rewritten per block and step)
+  float *n0_sc = nullptr, *n0_sh = nullptr;       // norm0 scale / shift of the current block (n_sc / n_sh: norm1)
+  float *t1_big = nullptr, *t1_int = nullptr;     // row sums of the forward DFT tables
+  double* sums0 = nullptr;                        // statistics of the NEXT block's input, gathered by the epilogue that writes it
   std::vector<Blk> blk;
   const float *mean, *stdv, *enc1_b, *enc2_b, *dec1_b, *dec2_b;
   float* pos_pm = nullptr;  // [P1, E]
@@ -345,7 +358,7 @@ struct SfnoEngine : Engine {
   double* sums;
   // scratch (engine owned, one member at a time)
   float *X, *Xn, *F1, *Rpm;
-  Img2 I_a, I_b, I_in;
+  Img2 I_a, I_b, I_in, I_x;   // hidden / GELU'd / input-state / block-input pixel images
   // spectral-chain data images: LI [m][lat][(ri,c)], SI [l][m][(ri,c)], MI / MI2 [m][l][(ro,o)], DI [lat][(m,ro)][o]
   Img2 LI, SI, MI, MI2, DI;
   bool scratch_ready = false;
@@ -401,10 +414,11 @@ struct SfnoEngine : Engine {
     return 0;
   }
   // instance norm folded into the pointwise GEMM that follows it:  W (sc * g + sh) + b = (W diag(sc)) g + (W sh + b)
-  int fold_norm(const W3& dst, float* bias_out, const float* Wsrc, const float* bias, int N, int K, cudaStream_t st) {
+  int fold_norm(const W3& dst, float* bias_out, const float* Wsrc, const float* bias, int N, int K, const float* sc,
+                const float* sh, cudaStream_t st) {
     int rc;
-    if ((rc = fill_w(dst, Wsrc, 0, N, K, 0, K, 1, n_sc, st))) return rc;
-    k_fold_bias<<<(N * 32 + 255) / 256, 256, 0, st>>>(Wsrc, n_sh, bias, bias_out, N, K);
+    if ((rc = fill_w(dst, Wsrc, 0, N, K, 0, K, 1, sc, st))) return rc;
+    k_fold_bias<<<(N * 32 + 255) / 256, 256, 0, st>>>(Wsrc, sh, bias, bias_out, N, K);
     count_launch();
     SKY_CUDA_OK(cudaGetLastError());
     return 0;
@@ -434,10 +448,15 @@ struct SfnoEngine : Engine {
     // transform tables as A operands (128-row tiles, [hi | hi | lo] along K)
     {
       const int r_dft = pad_to(2 * mmax, 128), r_l = pad_to(lmax, 128);
+      t1_big = dalloc<float>(r_dft); t1_int = dalloc<float>(r_dft);
+      if (!t1_big || !t1_int) return SKY_ERR_NOMEM;
       P(t, "dft.fwd_big", 2LL * mmax * W1);   // [(m,ri)][lon]
       if ((rc = pack_w(tdf_big, t, 0, 2 * mmax, W1, r_dft, 128, 1, 0, W1, 1, st))) return rc;
+      k_row_sums<<<(2 * mmax * 32 + 255) / 256, 256, 0, st>>>(t, 2 * mmax, W1, t1_big);
       P(t, "dft.fwd_int", 2LL * mmax * W2);
       if ((rc = pack_w(tdf_int, t, 0, 2 * mmax, W2, r_dft, 128, 1, 0, W2, 1, st))) return rc;
+      k_row_sums<<<(2 * mmax * 32 + 255) / 256, 256, 0, st>>>(t, 2 * mmax, W2, t1_int);
+      count_launch(2);
       P(t, "dft.inv_big", 2LL * mmax * W1);   // [lon][(m,ri)]
       if ((rc = pack_w(tdi_big, t, 0, W1, 2 * mmax, pad_to(W1, 128), 128, 1, 0, 2 * mmax, 1, st))) return rc;
       P(t, "dft.inv_int", 2LL * mmax * W2);
@@ -466,8 +485,9 @@ struct SfnoEngine : Engine {
         k_fold_inner_into_spec<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(const_cast<float*>(w), wi, total, E * E);
         count_launch();
         SKY_CUDA_OK(cudaGetLastError());
-      } else {
-        if ((rc = pack_w(b.inner, wi, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
+      } else {   // re-packed every step with norm0's scale folded in (fold_norm): keep the fp32 weights
+        KEEP(b.inner_w, N("inner.w"), (long long)E * E);
+        if ((rc = pack_w(b.inner, b.inner_w, 0, E, E, E, bn_point(E), 1, 0, E, 1, st))) return rc;
       }
       if ((rc = pack_w(b.spec, w, 1, 2 * E, 2 * E, 2 * E, bn_point(2 * E), lmax, 0, 0, 0, st))) return rc;
       const int Hd = cfg.mlp_ratio * E;
@@ -489,8 +509,9 @@ struct SfnoEngine : Engine {
     }
     in_sc = dalloc<float>(512); in_sh = dalloc<float>(512); n_sc = dalloc<float>(E); n_sh = dalloc<float>(E);
     sums = dalloc<double>(2 * E);
-    fc1_bs = dalloc<float>((size_t)cfg.mlp_ratio * E);
-    if (!in_sc || !in_sh || !n_sc || !n_sh || !sums || !fc1_bs) return SKY_ERR_NOMEM;
+    fc1_bs = dalloc<float>((size_t)cfg.mlp_ratio * E); inner_bs = dalloc<float>(E);
+    n0_sc = dalloc<float>(E); n0_sh = dalloc<float>(E); sums0 = dalloc<double>(2 * E);
+    if (!in_sc || !in_sh || !n_sc || !n_sh || !sums || !fc1_bs || !inner_bs || !n0_sc || !n0_sh || !sums0) return SKY_ERR_NOMEM;
     k_input_affine<<<1, 128, 0, st>>>(mean, stdv, Cin, in_sc, in_sh);
     count_launch();
     // ---- scratch ----
@@ -503,7 +524,7 @@ struct SfnoEngine : Engine {
     // zero padding) up to 63 rows past the grid
     const size_t ab = img_bytes(P1 + 128, (int)Hd);
     if (!img_alloc(I_a, ab) || !img_alloc(I_b, ab)) return SKY_ERR_NOMEM;
-    if (!img_alloc(I_in, img_bytes(P1, Cin))) return SKY_ERR_NOMEM;
+    if (!img_alloc(I_in, img_bytes(P1, Cin)) || !img_alloc(I_x, img_bytes(P1 + 128, E))) return SKY_ERR_NOMEM;
     if (!img_alloc(LI, img_bytes(H1, 2 * E, mmax))) return SKY_ERR_NOMEM;
     if (!img_alloc(SI, img_bytes(mmax, 2 * E, lmax))) return SKY_ERR_NOMEM;
     if (!img_alloc(MI, img_bytes(lmax, 2 * E, mmax)) || !img_alloc(MI2, img_bytes(lmax, 2 * E, mmax))) return SKY_ERR_NOMEM;
@@ -643,14 +664,16 @@ struct SfnoEngine : Engine {
   //   per m         S[l][(ri,c)] = Pf_m[l][lat]  * LI_m[lat][(ri,c)]      -> `to_mixing` as [l][m][(ri,c)] (A images of the
   //                 mixing GEMM) and / or `to_inverse` as [m][l][(ri,c)] (data of an inverse transform: the residual of a
   //                 grid-changing block); the second layout costs a second pass of the (cheap) Legendre GEMM
-  int forward_sht(const Img2& D, int Hi, int Wi, Img2* to_mixing, Img2* to_inverse, cudaStream_t st) {
+  int forward_sht(const Img2& D, int Hi, int Wi, const float* csc, const float* csh, Img2* to_mixing, Img2* to_inverse,
+                  cudaStream_t st) {
     const bool big = Hi == H1;
     const int n2 = 2 * E;
     int rc;
     const long long li_b = tile_img_bytes(Hi, n2);
     {
       BData bd{D.hi, D.lo, E / 64, Wi, 0};
-      EpiSplitRemap e{LI.hi, LI.lo, li_b, n2 / 64, 2, E, 1 << 30, 1, E};
+      // D holds the RAW block input; its instance norm (per-channel affine) is applied behind the linear transform
+      EpiSplitRemap e{LI.hi, LI.lo, li_b, n2 / 64, 2, E, 1 << 30, 1, E, 0, csc, csh, big ? t1_big : t1_int};
       if ((rc = gemm_tb(KT_SFNO_SHT, big ? tdf_big : tdf_int, bd, e, 2 * mmax, E, Hi, st))) return rc;
     }
     BData bd{LI.hi, LI.lo, n2 / 64, 0, li_b};
@@ -692,16 +715,20 @@ struct SfnoEngine : Engine {
     const long long Pi = (long long)Hi * Wi, Po = (long long)Ho * Wo;
     const int n2 = 2 * E, Hd = cfg.mlp_ratio * E;
     int rc;
-    // norm0 statistics of the block input
-    if ((rc = norm_stats(xin, Pi, 0, b.n0g, b.n0b, st))) return rc;
-    // pixel image of norm0(x) (hi / lo, K = channels): the data of the forward DFT and the A operand of the inner skip;
-    // on an unchanged grid its fp32 copy is the residual of the outer skip
+    // norm0 of the block input: its statistics were gathered by the epilogue that wrote xin (encoder fc2 / previous fc2);
+    // the affine is applied behind the forward DFT, inside the inner skip's weights and inside the outer skip's addend
+    prof_begin(KT_SFNO_MISC, st);
+    k_finalize_norm<<<(E + 127) / 128, 128, 0, st>>>(sums0, b.n0g, b.n0b, cfg.eps, Pi, E, n0_sc, n0_sh);
+    count_launch();
+    prof_end(KT_SFNO_MISC, st);
     if (Hi == Ho) {
-      if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st, Rpm, E))) return rc;
-      if ((rc = forward_sht(I_a, Hi, Wi, &SI, nullptr, st))) return rc;
+      if ((rc = forward_sht(I_x, Hi, Wi, n0_sc, n0_sh, &SI, nullptr, st))) return rc;
+      prof_begin(KT_SFNO_MISC, st);
+      rc = fold_norm(b.inner, inner_bs, b.inner_w, b.inner_b, E, E, n0_sc, n0_sh, st);
+      prof_end(KT_SFNO_MISC, st);
+      if (rc) return rc;
     } else {
-      if ((rc = pack(KT_SFNO_MISC, xin, I_a, 1, 1, (int)Pi, E, 0, 0, E, 2, 1, 2, n_sc, n_sh, 0, 0, 1, 2, 3, st))) return rc;
-      if ((rc = forward_sht(I_a, Hi, Wi, &SI, &MI2, st))) return rc;
+      if ((rc = forward_sht(I_x, Hi, Wi, n0_sc, n0_sh, &SI, &MI2, st))) return rc;
       // only the OUTER skip needs the resampled residual as a field; the inner skip lives in the mixing matrices
       if ((rc = inverse_sht(MI2, Ho, Wo, to_field(Rpm, Wo), st))) return rc;
     }
@@ -715,8 +742,8 @@ struct SfnoEngine : Engine {
     SKY_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * E * sizeof(double), st));
     if (Hi == Ho) {
       if ((rc = inverse_sht(MI, Ho, Wo, to_field(F1, Wo), st))) return rc;
-      EpiGeluStatsImg e{I_b.hi, I_b.lo, E / 64, b.inner_b, F1, E, 0, sums, E};
-      if ((rc = gemm_epi(KT_SFNO_MLP, I_a, E / 64, 0, 0, e, b.inner, Po, st))) return rc;
+      EpiGeluStatsImg e{I_b.hi, I_b.lo, E / 64, inner_bs, F1, E, 0, sums, E};
+      if ((rc = gemm_epi(KT_SFNO_MLP, I_x, E / 64, 0, 0, e, b.inner, Po, st))) return rc;
     } else {
       EpiGeluStatsImg e{I_b.hi, I_b.lo, E / 64, b.inner_b, nullptr, E, Wo, sums, E};
       if ((rc = inverse_sht(MI, Ho, Wo, e, st))) return rc;
@@ -725,12 +752,20 @@ struct SfnoEngine : Engine {
     prof_begin(KT_SFNO_MISC, st);
     k_finalize_norm<<<(E + 127) / 128, 128, 0, st>>>(sums, b.n1g, b.n1b, cfg.eps, Po, E, n_sc, n_sh);
     count_launch();
-    if ((rc = fold_norm(b.fc1, fc1_bs, b.fc1_w, b.fc1_b, Hd, E, st))) return rc;
+    if ((rc = fold_norm(b.fc1, fc1_bs, b.fc1_w, b.fc1_b, Hd, E, n_sc, n_sh, st))) return rc;
     prof_end(KT_SFNO_MISC, st);
     // GELU(fc1) goes straight into the operand images of fc2 (I_a: the residual image it held was consumed by the inner skip)
     if ((rc = gemm_to_img(KT_SFNO_MLP, I_b, E, Po, I_a, Hd, fc1_bs, true, b.fc1, st))) return rc;
-    // x_out = residual + fc2(...): the residual is an addend of the epilogue (no copy, no read-modify-write)
-    if ((rc = gemm(KT_SFNO_MLP, I_a, Hd, 0, Po, xout, E, 0, b.fc2_b, false, b.fc2, Po, st, Rpm))) return rc;
+    // x_out = residual + fc2(...): fp32 state + its pixel image (next block's data / the decoder's input) + the next
+    // block's norm0 statistics, all from this epilogue; the residual is norm0(xin) evaluated on the fly (unchanged grid) or
+    // the resampled field
+    SKY_CUDA_OK(cudaMemsetAsync(sums0, 0, 2 * E * sizeof(double), st));
+    {
+      const bool same = Hi == Ho;
+      EpiF32ImgStats e{i + 1 < L ? xout : nullptr, E, I_x.hi, I_x.lo, E / 64, b.fc2_b, same ? xin : Rpm, same ? n0_sc : nullptr, same ? n0_sh : nullptr,
+                       i + 1 < L ? sums0 : nullptr, E};
+      if ((rc = gemm_epi(KT_SFNO_MLP, I_a, Hd / 64, 0, 0, e, b.fc2, Po, st))) return rc;
+    }
     float* tmp = xin; xin = xout; xout = tmp;
     return 0;
   }
@@ -740,17 +775,21 @@ struct SfnoEngine : Engine {
     // encoder
     if ((rc = pack(KT_SFNO_ENC, x_in, I_in, 1, 1, (int)P1, Cin, 0, 0, 1, 2LL * P1, P1, 2, in_sc, in_sh, 0, 1, 0, 2, 3, st))) return rc;
     if ((rc = gemm_to_img(KT_SFNO_ENC, I_in, Cin, P1, I_a, E, enc1_b, true, enc1, st))) return rc;   // GELU(fc1) -> split images
-    if ((rc = gemm(KT_SFNO_ENC, I_a, E, 0, P1, X, E, 0, enc2_b, false, enc2, P1, st, pos_pm))) return rc;   // + positional embedding
+    SKY_CUDA_OK(cudaMemsetAsync(sums0, 0, 2 * E * sizeof(double), st));
+    {   // + positional embedding; fp32 state, pixel image and the first block's norm0 statistics from one epilogue
+      // (the fp32 copy is only read by an unchanged-grid first block's outer skip, i.e. when there is a single block)
+      EpiF32ImgStats e{L > 1 ? nullptr : X, E, I_x.hi, I_x.lo, E / 64, enc2_b, pos_pm, nullptr, nullptr, sums0, E};
+      if ((rc = gemm_epi(KT_SFNO_ENC, I_a, E / 64, 0, 0, e, enc2, P1, st))) return rc;
+    }
     float *a = X, *b = Xn;
     for (int i = 0; i < L; ++i)
       if ((rc = run_block(i, a, b, st))) return rc;
-    // decoder on concat(x, normalised input)
-    if ((rc = pack(KT_SFNO_DEC, a, I_a, 1, 1, (int)P1, E, 0, 0, E, 2, 1, 0, nullptr, nullptr, 0, 0, 1, 2, 3, st))) return rc;
+    // decoder on concat(x, normalised input): x is already there as the last fc2's pixel image
     {
       AOperand op;
       op.nseg = 6; op.m_tiles_per_batch = 0;
       const int kx = E / 64, ki = pad_to(Cin, 64) / 64;
-      const uint8_t* segs[6] = {I_a.hi, I_in.hi, I_a.lo, I_in.lo, I_a.hi, I_in.hi};
+      const uint8_t* segs[6] = {I_x.hi, I_in.hi, I_x.lo, I_in.lo, I_x.hi, I_in.hi};
       for (int s = 0; s < 6; ++s) { op.seg[s] = segs[s]; op.nkb[s] = (s & 1) ? ki : kx; op.batch_stride[s] = 0; }
       EpiSplitImg<true> e{I_b.hi, I_b.lo, E / 64, dec1_b, dec1.N};   // GELU(fc1) -> operand images of fc2
       if ((rc = gemm_op(KT_SFNO_DEC, op, e, dec1, P1, st))) return rc;
