@@ -57,6 +57,8 @@ k_gemm_tb(const uint8_t* __restrict__ Timg, long long t_batch_stride, const BDat
     mbar_fence_init();
   }
   if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if constexpr (has_cta_stats<Epi>::value)
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sbias[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -153,6 +155,7 @@ k_gemm_tb(const uint8_t* __restrict__ Timg, long long t_batch_stride, const BDat
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cta_stats_flush(epi, sbias);
   if (warp == MMAW) {
     __syncwarp();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -254,6 +257,7 @@ struct EpiSplitRemap {
 // statistics pass over it, and the GELU + normalise + split pack pass.  Pixel row = batch * rows_per_batch + row.
 struct EpiGeluStatsImg {
   static constexpr bool kNeedsBias = false;
+  static constexpr bool kCtaStats = true;   // n_valid <= 512
   uint8_t* hi; uint8_t* lo; int nkb;
   const float* bias;          // per column, may be null
   const float* add; int ld;   // fp32 addend [pixel][ld], may be null
@@ -324,8 +328,8 @@ struct EpiGeluStatsImg {
       if (rsub == 0 && cols_ok) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          atomicAdd(sums + col + e, (double)s[e]);
-          atomicAdd(sums + n_valid + col + e, (double)q[e]);
+          red_shared_f32(x.svec_s + (uint32_t)(col + e) * 4u, s[e]);
+          red_shared_f32(x.svec_s + (uint32_t)(512 + col + e) * 4u, q[e]);
         }
       }
       __syncwarp();
@@ -339,6 +343,7 @@ struct EpiGeluStatsImg {
 // decoder's input) and per-channel sum / sum of squares (the next block's norm0) in one pass.
 struct EpiF32ImgStats {
   static constexpr bool kNeedsBias = false;
+  static constexpr bool kCtaStats = true;   // n_valid <= 512
   float* out; int ld;          // out may be null when nothing reads the fp32 state (the image is always written)
   uint8_t* hi; uint8_t* lo; int nkb;
   const float* bias;
@@ -422,8 +427,8 @@ struct EpiF32ImgStats {
         if (rsub == 0 && cols_ok) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            atomicAdd(sums + col + e, (double)s[e]);
-            atomicAdd(sums + n_valid + col + e, (double)q[e]);
+            red_shared_f32(x.svec_s + (uint32_t)(col + e) * 4u, s[e]);
+            red_shared_f32(x.svec_s + (uint32_t)(512 + col + e) * 4u, q[e]);
           }
         }
       }
