@@ -20,6 +20,8 @@ struct AOperand {
   long long batch_stride[6];  // bytes between batches of each segment
   int nseg;
   int m_tiles_per_batch;      // row tiles of one batch inside a segment image
+  int tri = 0;                // 1: batch b only has rows 0 .. b (degree l of a spectrum holds orders m <= l): row tiles that
+                              // start past row b are skipped by every role (their output is multiplied by zeros downstream)
   __device__ const uint8_t* kblock(int batch, int mt, int kb) const {
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -100,6 +102,7 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
+      if (A.tri && mt * G2_BLOCK_M > b) continue;
       const uint8_t* wsrc = Wimg + (size_t)b * w_batch_stride + (size_t)nt * num_kb * Cfg::B_BYTES;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
@@ -116,9 +119,11 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
   } else if (warp == MMAW) {
     constexpr uint32_t idesc = make_idesc_f16(G2_BLOCK_M, Cfg::N_INST);
     int s = 0; uint32_t ph = 0; int it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (A.tri && (int)((tile % tiles_per_batch) / num_n_tiles) * G2_BLOCK_M > (int)(tile / tiles_per_batch)) continue;
       const int buf = it % Cfg::NBUF;
       const uint32_t use = (uint32_t)(it / Cfg::NBUF);
+      ++it;
       mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
@@ -153,10 +158,12 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
     ctx.patch_s = smem_u32(ctx.patch);
     ctx.svec_s = smem_u32(sbias);
     int it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
+      if (A.tri && (t / num_n_tiles) * G2_BLOCK_M > b) continue;
       const int buf = it % Cfg::NBUF;
       const uint32_t use = (uint32_t)(it / Cfg::NBUF);
-      const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
+      ++it;
       ctx.batch = b;
       ctx.row0 = (long long)(t / num_n_tiles) * G2_BLOCK_M + q * 32;
       ctx.n0 = (t % num_n_tiles) * BLOCK_N;

@@ -582,8 +582,9 @@ struct SfnoEngine : Engine {
   // D[batch][M, N] (=|+=) [hi|lo|hi](A) * W3^T (+bias)
   template <class Epi>
   int gemm_epi(int tag, const Img2& A, int nkbA, long long a_bstride, int a_mtiles, const Epi& epi, const W3& w,
-               long long M, cudaStream_t st) {
+               long long M, cudaStream_t st, int tri = 0) {
     AOperand a;
+    a.tri = tri;
     a.nseg = 3; a.m_tiles_per_batch = a_mtiles;
     a.seg[0] = A.hi; a.seg[1] = A.lo; a.seg[2] = A.hi;
     for (int s = 0; s < 3; ++s) { a.nkb[s] = nkbA; a.batch_stride[s] = a_bstride; }
@@ -735,7 +736,9 @@ struct SfnoEngine : Engine {
     // spectral channel mixing, one GEMM per degree l: rows m, K = (ri, i); written as the inverse Legendre's data [m][l][(ro,o)]
     {
       EpiSplitRemap e{MI.hi, MI.lo, tile_img_bytes(lmax, n2), n2 / 64, 1, 0, 1 << 30, 1, n2};
-      if ((rc = gemm_epi(KT_SFNO_SPEC, SI, n2 / 64, tile_img_bytes(mmax, n2), pad_to(mmax, 128) / 128, e, b.spec, mmax, st))) return rc;
+      // degree l only has orders m <= l: row tiles past l are skipped (what they would write meets zeros of the inverse
+      // Legendre table)
+      if ((rc = gemm_epi(KT_SFNO_SPEC, SI, n2 / 64, tile_img_bytes(mmax, n2), pad_to(mmax, 128) / 128, e, b.spec, mmax, st, 1))) return rc;
     }
     // g = GELU(iSHT(mixed) + inner_skip(residual) + bias) -> pixel image I_b + norm1 statistics, from the epilogue that
     // produces y (the inner-skip GEMM on an unchanged grid, the inverse DFT when the inner skip is folded)
