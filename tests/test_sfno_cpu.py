@@ -134,3 +134,38 @@ def test_full_size_fixtures_match_the_seeded_inputs():
         np.testing.assert_array_equal(x0[:, ::64, ::64], fx["x0_sample"])
         assert fx["y_sample"].shape == (len(names), 56, 85) and np.isfinite(fx["y_block"]).all()
         assert (fx["y_std"] > 0).all() and float(fx["oracle_seconds"]) > 1.0
+
+
+def test_engine_rewrites_are_identities_of_the_oracle():
+    """The CUDA engine restructures the block algebraically (skyrim_b200/csrc/sfno_engine.cu); each rewrite is checked here
+    on the fp64 oracle, so that the GPU parity tests measure rounding only:
+      1. grid-changing blocks: iSHT(W_l X) + V iSHT(X) + b = iSHT((W_l + V) X) + b  (inner skip folded into the mixing);
+      2. an instance norm in front of a 1x1 convolution folds into its weights:  W (sc*g + sh) + b = (W diag(sc)) g + (W sh + b);
+      3. the norm's affine commutes with the (linear, per-channel) forward transform:  SHT(sc*x + sh) = sc*SHT(x) + sh*SHT(1)."""
+    cfg = sfno_small(49, 96, embed=16, layers=3)
+    w = make_sfno_weights(cfg, 5)
+    x0 = synthetic_state(FCNV2_CHANNELS, cfg.nlat, cfg.nlon, 5)
+    ref = SFNORef(cfg, w, dtype=torch.float64)
+    y = ref.step(x0).numpy()
+    # 1. fold the inner skip of the first and last block into their mixing matrices, zero the pixel-space weights
+    wf = {k: np.array(v, dtype=np.float64) for k, v in w.items()}
+    for i in (0, cfg.layers - 1):
+        wf[f"blk{i}.spec.w"][..., 0] += wf[f"blk{i}.inner.w"][None]
+        wf[f"blk{i}.inner.w"][:] = 0.0
+    yf = SFNORef(cfg, wf, dtype=torch.float64).step(x0).numpy()
+    assert rel_err_per_channel(yf, y).max() < 1e-10
+    # 2. / 3. on one block's tensors
+    g = torch.randn(cfg.embed, cfg.h, cfg.w, dtype=torch.float64)
+    sc, sh = torch.rand(cfg.embed, dtype=torch.float64) + 0.5, torch.randn(cfg.embed, dtype=torch.float64)
+    W1, b1 = ref.w["blk1.fc1.w"], ref.w["blk1.fc1.b"]
+    lhs = ref._conv1x1(g * sc[:, None, None] + sh[:, None, None], W1, b1)
+    rhs = ref._conv1x1(g, W1 * sc[None, :], W1 @ sh + b1)
+    assert torch.allclose(lhs, rhs, rtol=1e-12, atol=1e-12)
+    X1 = ref.sht(torch.ones(1, cfg.h, cfg.w, dtype=torch.float64), "int")[0]
+    lhs = ref.sht(g * sc[:, None, None] + sh[:, None, None], "int")
+    rhs = ref.sht(g, "int") * sc[:, None, None] + sh[:, None, None] * X1[None]
+    assert torch.allclose(lhs, rhs, rtol=1e-11, atol=1e-11)
+    # ... and SHT(1) lives in the (l = 0, m = 0) coefficient alone: the engine adds sh * (row sum of the DFT table) to the
+    # m = 0 real row before the Legendre transform
+    mask = torch.ones_like(X1.real, dtype=torch.bool); mask[0, 0] = False
+    assert X1[mask].abs().max() < 1e-12 * X1[0, 0].abs()
