@@ -103,14 +103,16 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
       const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
       if (A.tri && mt * G2_BLOCK_M > b) continue;
-      const uint8_t* wsrc = Wimg + (size_t)b * w_batch_stride + (size_t)nt * num_kb * Cfg::B_BYTES;
+      // W image = [hi | lo] (nkw k-blocks each), consumed as hi, hi, lo against A = hi, lo, hi
+      const int nkw = num_kb / 3;
+      const uint8_t* wsrc = Wimg + (size_t)b * w_batch_stride + (size_t)nt * (2 * nkw) * Cfg::B_BYTES;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         if (lane == 0) {
           uint8_t* dst = smem + s * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
           bulk_g2s(dst, A.kblock(b, mt, kb), G2_A_BYTES, &full[s]);
-          bulk_g2s(dst + G2_A_BYTES, wsrc + (size_t)kb * Cfg::B_BYTES, Cfg::B_BYTES, &full[s]);
+          bulk_g2s(dst + G2_A_BYTES, wsrc + (size_t)(kb < nkw ? kb : kb - nkw) * Cfg::B_BYTES, Cfg::B_BYTES, &full[s]);
         }
         __syncwarp();
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }

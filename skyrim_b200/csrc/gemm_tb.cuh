@@ -2,8 +2,8 @@
 //
 //   for b in batches:  D_b[M, N] = T_b[M, Ktot] * X_b[Ktot, N]        -> fused epilogue
 //
-// A = a TABLE (DFT matrix, Legendre table of one zonal wavenumber): K-major tile image packed [hi | hi | lo] along K,
-//     128-row tiles (a W3 image with BN = 128), optionally one table per batch.
+// A = a TABLE (DFT matrix, Legendre table of one zonal wavenumber): K-major tile image packed [hi | lo] along K (read as
+//     hi, hi, lo), 128-row tiles (a W3 image with BN = 128), optionally one table per batch.
 // B = the DATA, used where it lies: an fp16 tile image whose ROWS are the contraction index (pixels of one latitude,
 //     latitudes, degrees l, (m, re/im)) and whose 128-byte row chunks hold 64 consecutive channels.  Those bytes are a
 //     valid MN-MAJOR SWIZZLE_128B B operand (tools/umma_probe.cu cases 3 and 7: atoms of [64 k-rows][128 B] stacked along
@@ -69,7 +69,7 @@ k_gemm_tb(const uint8_t* __restrict__ Timg, long long t_batch_stride, const BDat
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = (int)(tile / tiles_per_batch), t = (int)(tile % tiles_per_batch);
       const int mt = t / num_n_tiles, nt = t % num_n_tiles;
-      const uint8_t* tsrc = Timg + (size_t)b * t_batch_stride + (size_t)mt * num_kb * G2_A_BYTES;
+      const uint8_t* tsrc = Timg + (size_t)b * t_batch_stride + (size_t)mt * (2 * nkb) * G2_A_BYTES;   // [hi | lo] image
       const long long row_b = (long long)b * B.rows_per_batch;
       const size_t boff = (size_t)b * B.batch_bytes;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -77,7 +77,7 @@ k_gemm_tb(const uint8_t* __restrict__ Timg, long long t_batch_stride, const BDat
         uint8_t* dst = smem + s * Cfg::STAGE_BYTES;
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          bulk_g2s(dst, tsrc + (size_t)kb * G2_A_BYTES, G2_A_BYTES, &full[s]);
+          bulk_g2s(dst, tsrc + (size_t)(kb < nkb ? kb : kb - nkb) * G2_A_BYTES, G2_A_BYTES, &full[s]);   // hi, hi, lo
         }
         __syncwarp();
         // data rows [r0, r0 + 64) of segment hi | lo | hi; lanes 0 .. ATOMS-1 fetch one 64-channel atom each

@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(256) k_pack_tile(PackDesc d, int ext_d, int n_
 }
 
 // ======================================================================================
-// weights / tables -> 3-term W images  [batch][N/BN][3*Kp/64][BN x 128 B]   ([hi | hi | lo] along K)
+// weights / tables -> split W images  [batch][N/BN][2*Kp/64][BN x 128 B]   ([hi | lo] along K; the GEMM loaders read
+// the k-blocks in the order hi, hi, lo against the data's hi, lo, hi: the second pass over hi comes from L2)
 //   mode 0: src[b*s_b + n*s_n + k*s_k]            (n < n_valid, k < k_valid)
 //   mode 1: complex channel mixing: src = W[l][o][i][2]; row n = (ro, o), col k = (ri, i)  (re/im-major: the spectra
 //           are stored as [.., (ri, c)] so that 64 consecutive channels share a 128-byte row):
@@ -189,14 +190,13 @@ __global__ void __launch_bounds__(256) k_pack_w3(WPackDesc d, long long total) {
     h[e] = __float2half_rn(v);
     l[e] = __float2half_rn(v - __half2float(h[e]));
   }
-  const int nkb = d.Kp / 64, nkb3 = 3 * nkb;
+  const int nkb = d.Kp / 64, nkb2 = 2 * nkb;
   const int nt = n / d.BN, nr = n % d.BN, kb = kc / 8, ch = kc % 8;
   const size_t tile_bytes = (size_t)d.BN * 128;
-  uint8_t* base = d.img + (size_t)b * (d.N / d.BN) * nkb3 * tile_bytes + (size_t)nt * nkb3 * tile_bytes;
+  uint8_t* base = d.img + (size_t)b * (d.N / d.BN) * nkb2 * tile_bytes + (size_t)nt * nkb2 * tile_bytes;
   const uint32_t o = sw128_offset(nr, ch);
   *reinterpret_cast<uint4*>(base + (size_t)kb * tile_bytes + o) = *reinterpret_cast<uint4*>(h);
-  *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * tile_bytes + o) = *reinterpret_cast<uint4*>(h);
-  *reinterpret_cast<uint4*>(base + (size_t)(2 * nkb + kb) * tile_bytes + o) = *reinterpret_cast<uint4*>(l);
+  *reinterpret_cast<uint4*>(base + (size_t)(nkb + kb) * tile_bytes + o) = *reinterpret_cast<uint4*>(l);
 }
 
 // per-column sums of (optionally GELU'd) fp32 [P, E]:  sums[c], sums[E + c]  (instance norm).
@@ -398,7 +398,7 @@ struct SfnoEngine : Engine {
              long long s_n, long long s_k, cudaStream_t st) {
     w.N = N; w.Kp = pad_to(k_valid, 64); w.BN = BN; w.batches = batches;
     if (N % BN) { set_error("internal: N=%d not a multiple of BN=%d", N, BN); return SKY_ERR_STATE; }
-    w.batch_stride = (long long)N * 3 * w.Kp * 2;
+    w.batch_stride = (long long)N * 2 * w.Kp * 2;   // [hi | lo]
     w.img = dalloc<uint8_t>((size_t)w.batch_stride * batches);
     if (!w.img) return SKY_ERR_NOMEM;
     return fill_w(w, src, mode, n_valid, k_valid, s_b, s_n, s_k, nullptr, st);
