@@ -21,6 +21,7 @@ class FourcastnetV2Model(GlobalModel):
         from ...weights import make_sfno_weights, sfno_tables
         import os
         real = os.environ.get("SKYRIM_B200_WEIGHTS_FCNV2")
+        guard = self._weights is None and bool(real)
         if self._weights is None and real:
             # fcnv2_sm checkpoint directory (weights.tar + global_means.npy / global_stds.npy: what fcnv2_sm.load reads in
             # the reference, fourcastnet_v2.py:36-37); hyper-parameters come from the tensor shapes
@@ -30,4 +31,6 @@ class FourcastnetV2Model(GlobalModel):
         w = dict(self._weights if self._weights is not None else make_sfno_weights(self._cfg, self._seed))
         w.update(sfno_tables(self._cfg))
         eng.load_weights(w)
-        return SFNOTimeLoop(eng)
+        loop = SFNOTimeLoop(eng)
+        loop.guard_first_step = guard   # real checkpoint: first step of every rollout under the fp16-range guard
+        return loop

@@ -31,7 +31,11 @@ class PanguModel(GlobalModel):
         eng = StepEngine(self._cfg, self._device)
         # no network here: without SKYRIM_B200_WEIGHTS or a weight dict the engine runs on seeded synthetic weights
         eng.load_weights(w if w is not None else make_pangu_weights(self._cfg, self._seed))
-        return PanguTimeLoop(eng)
+        loop = PanguTimeLoop(eng)
+        # a real checkpoint feeds un-normalised residual streams to fp16 tensor-core operands: the first step of every
+        # rollout runs with the engine's fp16-range guard (StepEngine.step_guarded raises above 3e4)
+        loop.guard_first_step = bool(real) and self._weights is None
+        return loop
 
     @property
     def device(self):

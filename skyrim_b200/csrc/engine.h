@@ -37,6 +37,14 @@ struct Engine {
   std::vector<void*> kept;  // small persistent fp32 tensors (biases, norm vectors, masks): copies that outlive the arena
   bool loaded = false;
   int stop_after = 99;      // debug tap (sky_model_debug_set "stop_after"): return from step() after stage n
+  // fp16-range guard (sky_model_debug_set "range_guard" 1): the step scans the fp16 operand images it produced and keeps
+  // max |value| per class in range_dev[8] (read back with debug_copy "range").  The tensor cores take fp16 operands (5
+  // exponent bits): with real checkpoints the caller runs the first step of a rollout guarded and refuses anything > 3e4.
+  // Slots: 0 token images (LN outputs), 1 q/k/v, 2 attention output, 3 down / up-sampled images (Pangu);
+  //        4 pixel images, 5 hidden images, 6 spectral images (SFNO).
+  int range_guard = 0;
+  float* range_dev = nullptr;
+  int range_scan(int slot, const void* img, size_t bytes, cudaStream_t st);   // no-op unless range_guard
 
   // optional per-kernel timing: events are recorded around launches whose tag is in prof_mask
   uint64_t prof_mask = 0;

@@ -41,25 +41,26 @@ struct EpiCtxB : EpiCtx {
 // Epilogues that gather per-channel statistics keep them in shared memory for the CTA's whole (persistent) life and flush
 // them with ONE fp64 atomic per channel and CTA at kernel end: per-chunk global atomics (26 M on 768 addresses for a
 // full-resolution GEMM) were the bottleneck of those epilogues (ncu r2b: 2.0 ms against 1.07 ms for the same GEMM with a
-// plain store).  Layout of the CTA accumulators: sums at [0, 512), sums of squares at [512, 1024) of the bias region.
+// plain store).  Layout of the CTA accumulators (fp64): sums at [0, 384), sums of squares at [384, 768) of the bias region.
 template <class E, class = void> struct has_cta_stats : std::false_type {};
 template <class E> struct has_cta_stats<E, std::void_t<decltype(E::kCtaStats)>> : std::true_type {};
-__device__ __forceinline__ void red_shared_f32(uint32_t addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+constexpr int CTA_STATS_MAX = 384;   // channels: 2 x 384 fp64 accumulators fill the 6 KB bias region
+// fp64 accumulators: the order in which the warps of a CTA (and then the CTAs) add their fp32 partial sums is not fixed;
+// in fp64 the order changes the result by ~1e-16 relative, i.e. the fp32 scale / shift derived from it are reproducible
+// from run to run (fp32 accumulators were not: 1e-7 differences in the statistics)
+__device__ __forceinline__ void red_shared_f64(uint32_t addr, double v) {
+  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 template <class Epi>
 __device__ __forceinline__ void cta_stats_flush(const Epi& epi, const float* sbias) {
   if constexpr (has_cta_stats<Epi>::value) {
     if (epi.sums) {
-      for (int i = threadIdx.x; i < 2 * epi.n_valid; i += blockDim.x) {
-        const int c = i < epi.n_valid ? i : i - epi.n_valid;
-        const float v = sbias[(i < epi.n_valid ? 0 : 512) + c];
-        atomicAdd(epi.sums + i, (double)v);
-      }
+      const double* acc = reinterpret_cast<const double*>(sbias);
+      for (int i = threadIdx.x; i < 2 * epi.n_valid; i += blockDim.x)
+        atomicAdd(epi.sums + i, acc[(i < epi.n_valid ? 0 : CTA_STATS_MAX) + (i < epi.n_valid ? i : i - epi.n_valid)]);
     }
   }
 }
-
 
 template <class Epi, int BLOCK_N, int EPI_WARPS>
 __global__ void __launch_bounds__((EPI_WARPS + 2) * 32, 1)
@@ -91,7 +92,7 @@ k_gemm_batched(const AOperand A, const Epi epi, const uint8_t* __restrict__ Wimg
   }
   if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   if constexpr (has_cta_stats<Epi>::value)
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sbias[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * 512; i += blockDim.x) sbias[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

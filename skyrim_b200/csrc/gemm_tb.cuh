@@ -58,7 +58,7 @@ k_gemm_tb(const uint8_t* __restrict__ Timg, long long t_batch_stride, const BDat
   }
   if (warp == MMAW) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   if constexpr (has_cta_stats<Epi>::value)
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sbias[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * 512; i += blockDim.x) sbias[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -257,7 +257,7 @@ struct EpiSplitRemap {
 // statistics pass over it, and the GELU + normalise + split pack pass.  Pixel row = batch * rows_per_batch + row.
 struct EpiGeluStatsImg {
   static constexpr bool kNeedsBias = false;
-  static constexpr bool kCtaStats = true;   // n_valid <= 512
+  static constexpr bool kCtaStats = true;   // n_valid <= CTA_STATS_MAX
   uint8_t* hi; uint8_t* lo; int nkb;
   const float* bias;          // per column, may be null
   const float* add; int ld;   // fp32 addend [pixel][ld], may be null
@@ -328,8 +328,8 @@ struct EpiGeluStatsImg {
       if (rsub == 0 && cols_ok) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          red_shared_f32(x.svec_s + (uint32_t)(col + e) * 4u, s[e]);
-          red_shared_f32(x.svec_s + (uint32_t)(512 + col + e) * 4u, q[e]);
+          red_shared_f64(x.svec_s + (uint32_t)(col + e) * 8u, (double)s[e]);
+          red_shared_f64(x.svec_s + (uint32_t)(CTA_STATS_MAX + col + e) * 8u, (double)q[e]);
         }
       }
       __syncwarp();
@@ -343,7 +343,7 @@ struct EpiGeluStatsImg {
 // decoder's input) and per-channel sum / sum of squares (the next block's norm0) in one pass.
 struct EpiF32ImgStats {
   static constexpr bool kNeedsBias = false;
-  static constexpr bool kCtaStats = true;   // n_valid <= 512
+  static constexpr bool kCtaStats = true;   // n_valid <= CTA_STATS_MAX
   float* out; int ld;          // out may be null when nothing reads the fp32 state (the image is always written)
   uint8_t* hi; uint8_t* lo; int nkb;
   const float* bias;
@@ -427,8 +427,8 @@ struct EpiF32ImgStats {
         if (rsub == 0 && cols_ok) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            red_shared_f32(x.svec_s + (uint32_t)(col + e) * 4u, s[e]);
-            red_shared_f32(x.svec_s + (uint32_t)(512 + col + e) * 4u, q[e]);
+            red_shared_f64(x.svec_s + (uint32_t)(col + e) * 8u, (double)s[e]);
+            red_shared_f64(x.svec_s + (uint32_t)(CTA_STATS_MAX + col + e) * 8u, (double)q[e]);
           }
         }
       }

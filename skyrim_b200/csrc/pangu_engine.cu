@@ -442,6 +442,12 @@ struct PanguEngine : Engine {
       prof_end(tag, st);
       if (rc) return rc;
     }
+    if (range_guard) {   // fp16 operand images of this block (whole tiles only: the tail rows of the last tile are never written)
+      const size_t full = (size_t)(R / 128) * nkb * G2_A_BYTES;
+      if ((rc = range_scan(0, xh, full, st))) return rc;
+      if ((rc = range_scan(1, ws.qkv, (size_t)3 * part_stride, st))) return rc;
+      if ((rc = range_scan(2, ws.atth, full, st))) return rc;
+    }
     return 0;
   }
 
@@ -483,6 +489,7 @@ struct PanguEngine : Engine {
       AImage A{ws.hidh, ws.hidh, 4 * C / 64, 0};
       Epi2F32Img<false, false> e{ws.x2, 2 * C, ws.x2h, 2 * C / 64, nullptr, nullptr, nullptr, 0.f};
       if ((rc = gemm2<192, 8>(KT_DOWN, A, e, down, R2, ws.scratch, st))) return rc;
+      if ((rc = range_scan(3, ws.x2h, (size_t)(R2 / 128) * (2 * C / 64) * G2_A_BYTES, st))) return rc;
     }
     if (stop == 2) return 0;
     for (int li = 1; li <= 2; ++li) {
@@ -529,6 +536,9 @@ struct PanguEngine : Engine {
       k_image_to_rows<<<(unsigned)((rows * cols + 255) / 256), 256, 0, st>>>(img, cols / 64, dst, rows, cols);
       SKY_CUDA_OK(cudaGetLastError());
       return 0;
+    } else if (!strcmp(what, "range")) {
+      if (!range_dev || max_floats < 8) { set_error("range guard is off (debug_set range_guard 1) or destination < 8 floats"); return SKY_ERR_STATE; }
+      src = range_dev; n = 8;
     } else { set_error("unknown debug buffer '%s'", what); return SKY_ERR_ARG; }
     if (n > max_floats) n = max_floats;
     SKY_CUDA_OK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));

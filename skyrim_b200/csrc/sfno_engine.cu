@@ -769,6 +769,15 @@ struct SfnoEngine : Engine {
                        i + 1 < L ? sums0 : nullptr, E};
       if ((rc = gemm_epi(KT_SFNO_MLP, I_a, Hd / 64, 0, 0, e, b.fc2, Po, st))) return rc;
     }
+    if (range_guard) {   // fp16 (hi) operand images this block produced: pixel images, hidden image, spectral images
+      if ((rc = range_scan(4, I_x.hi, (size_t)(Po / 128) * (E / 64) * G2_A_BYTES, st))) return rc;
+      if ((rc = range_scan(4, I_b.hi, (size_t)(Po / 128) * (E / 64) * G2_A_BYTES, st))) return rc;
+      if ((rc = range_scan(5, I_a.hi, (size_t)(Po / 128) * (Hd / 64) * G2_A_BYTES, st))) return rc;
+      if ((rc = range_scan(6, SI.hi, SI.bytes, st))) return rc;
+      if ((rc = range_scan(6, MI.hi, MI.bytes, st))) return rc;
+      if ((rc = range_scan(6, LI.hi, (size_t)mmax * tile_img_bytes(Hi, n2), st))) return rc;
+      if ((rc = range_scan(6, DI.hi, (size_t)Ho * tile_img_bytes(2 * mmax, E), st))) return rc;
+    }
     float* tmp = xin; xin = xout; xout = tmp;
     return 0;
   }
@@ -813,13 +822,19 @@ struct SfnoEngine : Engine {
     return 0;
   }
 
-  int debug_copy(const char* what, float*, uint64_t, void*, int, cudaStream_t) override {
+  int debug_copy(const char* what, float* dst, uint64_t max_floats, void*, int, cudaStream_t st) override {
+    if (!strcmp(what, "range")) {
+      if (!range_dev || max_floats < 8) { set_error("range guard is off (debug_set range_guard 1) or destination < 8 floats"); return SKY_ERR_STATE; }
+      SKY_CUDA_OK(cudaMemcpyAsync(dst, range_dev, 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
     set_error("unknown debug buffer '%s'", what);
     return SKY_ERR_ARG;
   }
 };
 
 Engine* make_sfno_engine(const sky_sfno_config_t& cfg, int device) {
+  if (cfg.embed > CTA_STATS_MAX) { set_error("unsupported SFNO shape: embed %d > %d", cfg.embed, CTA_STATS_MAX); return nullptr; }
   if (cfg.embed % 64 || cfg.nlat % cfg.scale_factor == 0 /* nlat = s*h + 1 */ || cfg.nlon % cfg.scale_factor ||
       (cfg.nlon / cfg.scale_factor) % 32 || (cfg.nlat / cfg.scale_factor) % 16 || cfg.n_channels > 128) {
     set_error("unsupported SFNO shape: nlat=%d nlon=%d embed=%d scale=%d", cfg.nlat, cfg.nlon, cfg.embed, cfg.scale_factor);

@@ -1,4 +1,5 @@
 // C-ABI entry points (include/skyrim_b200.h) + engine base plumbing + IC perturbation.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -25,7 +26,7 @@ void Engine::drop_graphs() {
 
 int Engine::step_cached(const float* x_in, float* x_out, int batch, void* ws, size_t ws_bytes, cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (!use_graphs || prof_mask != 0 || stop_after != 99 || cudaStreamIsCapturing(st, &cs) != cudaSuccess ||
+  if (!use_graphs || prof_mask != 0 || stop_after != 99 || range_guard || cudaStreamIsCapturing(st, &cs) != cudaSuccess ||
       cs != cudaStreamCaptureStatusNone)
     return step(x_in, x_out, batch, ws, ws_bytes, st);
   GraphEntry* e = nullptr;
@@ -69,6 +70,35 @@ Engine::~Engine() {
   for (void* p : kept) cudaFree(p);
   for (auto e : prof_pool) cudaEventDestroy(e);
   for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+}
+
+
+// max |h| over an fp16 buffer -> *slot (atomic max on the bits of a non-negative float; NaN counts as +inf)
+__global__ void __launch_bounds__(256) k_absmax_half(const uint4* __restrict__ p, size_t n16, float* __restrict__ slot) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      const float2 f = __half22float2(h);
+      const float a = fabsf(f.x), b = fabsf(f.y);
+      m = fmaxf(m, (a == a) ? a : __int_as_float(0x7f800000));
+      m = fmaxf(m, (b == b) ? b : __int_as_float(0x7f800000));
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(slot), __float_as_int(m));
+}
+int Engine::range_scan(int slot, const void* img, size_t bytes, cudaStream_t st) {
+  if (!range_guard || !range_dev || !img || bytes < 16) return 0;
+  const size_t n16 = bytes / 16;
+  const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 8);
+  k_absmax_half<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(img), n16, range_dev + slot);
+  SKY_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 const char* ktag_name(int t) {
@@ -143,6 +173,15 @@ const float* Engine::keep(const char* name, uint64_t expect, cudaStream_t st) {
 int Engine::debug_set(const char* key, long long value) {
   if (!strcmp(key, "stop_after")) { stop_after = (int)value; return 0; }
   if (!strcmp(key, "use_graphs")) { use_graphs = value != 0; return 0; }
+  if (!strcmp(key, "range_guard")) {
+    range_guard = value != 0;
+    if (range_guard && !range_dev) {
+      if (cudaMalloc(&range_dev, 8 * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc failed"); return SKY_ERR_NOMEM; }
+      kept.push_back(range_dev);
+    }
+    if (range_dev) SKY_CUDA_OK(cudaMemset(range_dev, 0, 8 * sizeof(float)));
+    return 0;
+  }
   set_error("unknown debug key '%s'", key);
   return SKY_ERR_ARG;
 }

@@ -122,6 +122,33 @@ class StepEngine:
                                                    self._workspace(batch).data_ptr(), batch, st), "debug_copy", self._L)
         return out
 
+    RANGE_SLOTS = ("token_images", "qkv", "attention_out", "resampled_images", "pixel_images", "hidden_images",
+                   "spectral_images", "unused")
+    FP16_LIMIT = 3.0e4
+
+    def step_guarded(self, x_in, x_out=None, limit: float | None = None):
+        """One step with the fp16-range guard on: the engine scans every fp16 operand image it produces (the tensor cores
+        take 5-exponent-bit operands) and this call raises if any |value| exceeds ``limit`` (default 3e4) or is not finite.
+        Meant for the FIRST step of a rollout with real checkpoints (synthetic weights keep every activation O(1)); the
+        guarded step runs with plain launches and a few extra reduction kernels.  Returns (x_out, {class: max |value|})."""
+        limit = self.FP16_LIMIT if limit is None else limit
+        self.debug_set("range_guard", 1)
+        try:
+            y = self.step(x_in, x_out)
+            r = self.torch.empty(8, dtype=self.torch.float32, device=f"cuda:{self.device}")
+            st = self.torch.cuda.current_stream(self.device).cuda_stream
+            _ffi.check(self._L.sky_model_debug_copy(self._h, b"range", r.data_ptr(), 8, self._workspace(x_in.shape[0]).data_ptr(),
+                                                    x_in.shape[0], st), "debug_copy(range)", self._L)
+            vals = r.cpu().tolist()
+        finally:
+            self.debug_set("range_guard", 0)
+        ranges = {n: v for n, v in zip(self.RANGE_SLOTS, vals) if v != 0.0}
+        bad = {n: v for n, v in ranges.items() if not (v <= limit)}
+        if bad:
+            raise _ffi.SkyError(f"fp16 operand range exceeded (limit {limit:g}): {bad}; this checkpoint needs operand scaling "
+                                f"the engine does not implement")
+        return y, ranges
+
     def debug_set(self, key: str, value: int):
         """test taps (never environment variables): e.g. ``debug_set("stop_after", 3)``"""
         _ffi.check(self._L.sky_model_debug_set(self._h, key.encode(), int(value)), "debug_set", self._L)

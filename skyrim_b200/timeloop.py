@@ -50,6 +50,9 @@ class _EngineTimeLoop:
         self._dev_in = None
         self._dev_out = None
         self._host_out = None
+        # real checkpoints (SKYRIM_B200_WEIGHTS*): the first step of every rollout runs with the fp16-range guard
+        self.guard_first_step = False
+        self.last_ranges = None
 
     # earth2mip TimeLoops accept .to(device); ours is pinned to its GPU (ensemble.py:34,46 calls these)
     def to(self, device):
@@ -66,8 +69,13 @@ class _EngineTimeLoop:
         cur = x[:, -1].to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         yield time, cur.clone(), None
         nxt = torch.empty_like(cur)
+        first = self.guard_first_step
         while True:
-            self.engine.step(cur, nxt)
+            if first:
+                _, self.last_ranges = self.engine.step_guarded(cur, nxt)
+                first = False
+            else:
+                self.engine.step(cur, nxt)
             time = time + self.time_step
             yield time, nxt, None
             cur, nxt = nxt, torch.empty_like(cur)  # the yielded tensor stays valid for the caller
@@ -93,7 +101,11 @@ class _EngineTimeLoop:
         copied = torch.cuda.Event()
         done[0].record(main)
         if n_steps > 0:
-            self.engine.step(ring[0], ring[1]); done[1].record(main)
+            if self.guard_first_step:
+                _, self.last_ranges = self.engine.step_guarded(ring[0], ring[1])
+            else:
+                self.engine.step(ring[0], ring[1])
+            done[1].record(main)
         for n in range(n_steps + 1):
             if 0 < n < n_steps:   # launch step n+1 before waiting for the copy of step n
                 self.engine.step(ring[n % 3], ring[(n + 1) % 3]); done[(n + 1) % 3].record(main)

@@ -61,3 +61,46 @@ def test_iter_host_matches_device_resident_chain():
         for (t, h), w in zip(got, want):
             assert torch.equal(h, w)
     eng.close()
+
+
+@pytest.mark.parametrize("model", ["pangu", "sfno"])
+def test_fp16_range_guard(model):
+    """The guarded step reports max |value| of every fp16 operand image class (O(1) on synthetic weights) and refuses
+    weights that push an operand past the fp16 range."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from skyrim_b200 import _ffi
+    from skyrim_b200.config import FCNV2_CHANNELS, PANGU_CHANNELS, pangu_small, sfno_small
+    from skyrim_b200.engine import StepEngine
+    from skyrim_b200.weights import make_pangu_weights, make_sfno_weights, sfno_tables, synthetic_state
+    if model == "pangu":
+        cfg, ch = pangu_small(41, 96), PANGU_CHANNELS
+        w = make_pangu_weights(cfg, 0)
+        big = "layer0.block0.qkv.w"
+    else:
+        cfg, ch = sfno_small(49, 96, embed=64, layers=3), FCNV2_CHANNELS
+        w = make_sfno_weights(cfg, 0)
+        big = "blk1.fc1.w"
+    assert big in w, sorted(w)[:20]
+    x = torch.from_numpy(synthetic_state(ch, cfg.nlat, cfg.nlon, 0))[None].cuda()
+
+    def engine(weights):
+        eng = StepEngine(cfg, 0)
+        allw = dict(weights)
+        if model == "sfno":
+            allw.update(sfno_tables(cfg))
+        eng.load_weights(allw)
+        return eng
+
+    eng = engine(w)
+    y_plain = eng.step(x).clone()
+    y, ranges = eng.step_guarded(x)
+    assert torch.equal(y, y_plain)                       # the guard only observes
+    assert ranges and all(0.0 < v < 1.0e3 for v in ranges.values()), ranges
+    eng.close()
+    w2 = dict(w)
+    w2[big] = w[big] * 1.0e6                              # one projection far outside what fp16 operands can hold
+    eng = engine(w2)
+    with pytest.raises(_ffi.SkyError, match="fp16 operand range"):
+        eng.step_guarded(x)
+    eng.close()

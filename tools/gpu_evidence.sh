@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round-end evidence on one B200 (run through gpurun): the bench line, the ncu launch lists of the bench command, and
-# `ncu --set full` captures of the dominant kernels.  Everything lands in gpurun_out/; the summaries are copied to profiles/.
+# `ncu --set full` captures of the dominant kernels.  Everything lands in gpurun_out/ (gpurun brings back at most 64 MiB:
+# keep the number of captured launches small); the summaries are copied to profiles/.
 tag=${1:-r2}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/${tag}_bench_final.json 2> gpurun_out/${tag}_bench_final.err
@@ -14,8 +15,10 @@ $NCU --set full --import-source on -k regex:k_mlp_fused_pair --launch-skip 1 -c 
     python tools/gpu_one_step.py 1 > gpurun_out/ncu_m.log 2>&1
 $NCU --set full --import-source on -k regex:k_window_attention_tc --launch-skip 1 -c 2 -f -o gpurun_out/${tag}_attn_full \
     python tools/gpu_one_step.py 1 > gpurun_out/ncu_a.log 2>&1
-$NCU --set full --import-source on -k regex:k_gemm_pair -c 4 -f -o gpurun_out/${tag}_qkv_full \
-    python tools/gpu_one_step.py 1 > gpurun_out/ncu_q.log 2>&1
-$NCU --set full -k regex:k_gemm_batched --launch-skip 40 -c 12 -f -o gpurun_out/${tag}_sfno_gemm_full \
-    python tools/gpu_sfno.py full > gpurun_out/ncu_s.log 2>&1
-ls -la gpurun_out | tail -20
+$NCU --set full -k regex:k_gemm_tb -c 5 -f -o gpurun_out/${tag}_sfno_tb_full \
+    python tools/gpu_sfno_one_step.py 1 > gpurun_out/ncu_s1.log 2>&1
+$NCU --set full -k regex:k_gemm_batched -c 4 -f -o gpurun_out/${tag}_sfno_gb_full \
+    python tools/gpu_sfno_one_step.py 1 > gpurun_out/ncu_s2.log 2>&1
+$NCU --set full -k regex:k_gemm_batched --launch-skip 48 -c 3 -f -o gpurun_out/${tag}_sfno_gb2_full \
+    python tools/gpu_sfno_one_step.py 1 > gpurun_out/ncu_s3.log 2>&1
+du -sh gpurun_out; ls -la gpurun_out | tail -20
