@@ -37,7 +37,8 @@ for rep in sys.argv[1:]:
             if "bytes" in key:
                 cells.append("%.0f" % to_mb(v, units[i]))
             elif key.startswith("gpu__time"):
-                f = float(v.replace(",", "")); f = f / 1000 if units[i] in ("nsecond", "ns") else f
+                f = float(v.replace(",", ""))
+                f *= {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6}.get(units[i], 1.0)
                 cells.append("%.0f" % f)
             else:
                 cells.append(v.split(".")[0] if key.startswith("launch") else "%.1f" % float(v.replace(",", "")))
