@@ -27,7 +27,7 @@ extern "C" {
 
 #define SKY_ABI_VERSION 1
 
-enum { SKY_MODEL_PANGU6 = 1, SKY_MODEL_SFNO73 = 2 };
+enum { SKY_MODEL_PANGU6 = 1, SKY_MODEL_SFNO73 = 2, SKY_MODEL_GRAPHCAST = 3 };
 enum { SKY_OK = 0, SKY_ERR_ARG = -1, SKY_ERR_CUDA = -2, SKY_ERR_STATE = -3, SKY_ERR_NOMEM = -4 };
 
 /* Pangu-Weather 6-h operator shape (patch (2,4,4) and window (2,6,12) are fixed).
@@ -53,6 +53,24 @@ typedef struct {
   int32_t mlp_ratio;       /* 2 */
   float eps;               /* instance-norm epsilon */
 } sky_sfno_config_t;
+
+/* GraphCast (operational 0.25 deg / 13 levels) operator shape; replaces what
+ * graphcast.load_time_loop_operational reads from the checkpoint and builds as mesh tables
+ * (/root/reference/skyrim/core/models/graphcast.py:51-54).  The graph itself (edge lists, edge / node features)
+ * travels in the weight arena as entries named "graph.*" (skyrim_b200/icomesh.py); the counts below size them. */
+typedef struct {
+  int32_t nlat, nlon;      /* 721, 1440 */
+  int32_t n_mesh;          /* 40962 multimesh nodes (icosahedron refined 6 times) */
+  int32_t n_mesh_edges;    /* 327660 directed multimesh edges, sorted by receiver */
+  int32_t n_g2m_edges;     /* grid2mesh edges, sorted by receiver (mesh node) */
+  int32_t latent;          /* 512 */
+  int32_t layers;          /* 16 processor layers */
+  int32_t n_state;         /* 83 channels per time slice: 82 prognostic + toa radiation (graphcast.py:17-41) */
+  int32_t n_prog;          /* 82 */
+  int32_t n_static;        /* 2: geopotential at the surface, land-sea mask */
+  int32_t dt_hours;        /* 6 */
+  float ln_eps;            /* 1e-5 */
+} sky_graphcast_config_t;
 
 /* one named fp32 tensor inside a flat weight arena */
 typedef struct {
@@ -94,6 +112,17 @@ SKY_API size_t sky_model_workspace_bytes(const sky_model_t* m, int32_t batch);
  * Replaces one `next()` of the TimeLoop generator (utils.py:34). */
 SKY_API int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batch, void* workspace,
                    size_t workspace_bytes, void* stream);
+
+/* Valid time (unix seconds, UTC) of the LAST time slice of the state the next sky_model_step starts from.  Operators
+ * with time-dependent forcings (GraphCast: toa radiation, year / day progress) keep this clock on the device and advance
+ * it by one step per sky_model_step, so a rollout sets it once; the others ignore it.
+ * Replaces the `time` argument of `stepper.initialize(x, time)` (graphcast.py:110). */
+SKY_API int sky_model_set_clock(sky_model_t* m, double unix_seconds, void* stream);
+
+/* Top-of-atmosphere incident solar radiation of the hour ending at `unix_seconds` [J m^-2] on the (nlat, nlon) grid
+ * (lat 90 -> -90, lon 0 -> 360): the forcing channel the reference calls "tp06" (graphcast.py:16,40).  `out` is device
+ * fp32 (nlat * nlon).  Used to fill that channel of an initial condition. */
+SKY_API int sky_toa_radiation(float* out, int32_t nlat, int32_t nlon, double unix_seconds, void* stream);
 
 /* Intermediate tensor taps for kernel-level parity tests: after a step, copy the named
  * internal buffer ("embed"/"tokens1"/"tokens2"...) of the LAST step into dst (device fp32). */

@@ -17,6 +17,7 @@ DEV_LIB_PATH = Path(__file__).resolve().parent / "libskyrim_b200_dev.so"
 
 SKY_MODEL_PANGU6 = 1
 SKY_MODEL_SFNO73 = 2
+SKY_MODEL_GRAPHCAST = 3
 
 
 class SkyError(RuntimeError):
@@ -35,6 +36,12 @@ class SFNOConfigC(C.Structure):
                 ("eps", C.c_float)]
 
 
+class GraphCastConfigC(C.Structure):
+    _fields_ = [("nlat", C.c_int32), ("nlon", C.c_int32), ("n_mesh", C.c_int32), ("n_mesh_edges", C.c_int32),
+                ("n_g2m_edges", C.c_int32), ("latent", C.c_int32), ("layers", C.c_int32), ("n_state", C.c_int32),
+                ("n_prog", C.c_int32), ("n_static", C.c_int32), ("dt_hours", C.c_int32), ("ln_eps", C.c_float)]
+
+
 class ParamDesc(C.Structure):
     _fields_ = [("name", C.c_char * 96), ("offset", C.c_uint64), ("count", C.c_uint64)]
 
@@ -48,6 +55,8 @@ EXPORTS = {
     "sky_model_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
     "sky_model_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t,
                                  C.c_void_p]),
+    "sky_model_set_clock": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "sky_toa_radiation": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p]),
     "sky_model_debug_copy": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32,
                                        C.c_void_p]),
     "sky_model_debug_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

@@ -136,3 +136,53 @@ def sfno_full() -> SFNOConfig:
 
 def sfno_small(nlat: int = 49, nlon: int = 96, embed: int = 64, layers: int = 3) -> SFNOConfig:
     return SFNOConfig(nlat=nlat, nlon=nlon, embed=embed, layers=layers)
+
+
+# ----------------------------------------------------------------------------------------
+# GraphCast (operational 0.25 deg / 13 levels)
+# ----------------------------------------------------------------------------------------
+GRAPHCAST_LEVELS = [50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000]
+# Order in which the reference flattens the stepper's Dataset (/root/reference/skyrim/core/models/graphcast.py:29-41
+# CHANNEL_MAP, applied by _to_global_da :68-91): q, z, t, u, v, w on 13 levels, then t2m, u10m, v10m, msl and the
+# forcing the reference labels "tp06" (it is toa_incident_solar_radiation, :16,40).  The CHANNELS list at :17-26 holds
+# the same 83 names with z first; the reference's own test compares them as sets (tests/core/test_graphcast.py:22).
+GRAPHCAST_CHANNELS = [f"{v}{p}" for v in "qztuvw" for p in GRAPHCAST_LEVELS] + ["t2m", "u10m", "v10m", "msl", "tp06"]
+
+
+@dataclass(frozen=True)
+class GraphCastConfig:
+    """GraphCast encoder - processor - decoder: latent 512, 16 message-passing layers on the
+    refinement-6 multimesh, one-hidden-layer swish MLPs with LayerNorm, sum aggregation."""
+    nlat: int = 721
+    nlon: int = 1440
+    mesh_levels: int = 6
+    latent: int = 512
+    layers: int = 16
+    radius_frac: float = 0.6
+    n_state: int = 83            # channels of ONE time slice of the state (82 prognostic + toa radiation)
+    n_prog: int = 82             # prognostic channels (inputs at t-6h and t, outputs as residuals)
+    n_static: int = 2            # geopotential at the surface, land-sea mask
+    ln_eps: float = 1e-5
+    dt_hours: int = 6
+
+    @property
+    def n_channels(self):        # channels of the stepped state tensor: (2 time slices) x n_state
+        return 2 * self.n_state
+
+    @property
+    def n_features(self):
+        """grid-node input features: 2 x prognostic, toa at (t-6h, t, t+6h), (year, day) x (sin, cos) at the three
+        times, statics, (cos lat, sin lon, cos lon)"""
+        return 2 * self.n_prog + 3 + 12 + self.n_static + 3
+
+    @property
+    def n_grid(self):
+        return self.nlat * self.nlon
+
+
+def graphcast_full() -> GraphCastConfig:
+    return GraphCastConfig()
+
+
+def graphcast_small(nlat: int = 41, nlon: int = 96, mesh_levels: int = 2, latent: int = 512, layers: int = 2) -> GraphCastConfig:
+    return GraphCastConfig(nlat=nlat, nlon=nlon, mesh_levels=mesh_levels, latent=latent, layers=layers)

@@ -19,7 +19,8 @@ void set_error(const char* fmt, ...);
 
 // kernel families, used for per-kernel CUDA-event timing (bench.py roofline) and launch counting
 enum KTag { KT_EMBED = 0, KT_QKV, KT_ATTN, KT_PROJ, KT_FC1, KT_FC2, KT_MLP, KT_DOWN, KT_UP, KT_RECOVER, KT_COPY,
-            KT_SFNO_ENC, KT_SFNO_SHT, KT_SFNO_SPEC, KT_SFNO_ISHT, KT_SFNO_MLP, KT_SFNO_DEC, KT_SFNO_MISC, KT_COUNT };
+            KT_SFNO_ENC, KT_SFNO_SHT, KT_SFNO_SPEC, KT_SFNO_ISHT, KT_SFNO_MLP, KT_SFNO_DEC, KT_SFNO_MISC,
+            KT_GC_FEAT, KT_GC_HIDDEN, KT_GC_LN, KT_GC_TABLE, KT_GC_AGG, KT_GC_OUT, KT_GC_MISC, KT_COUNT };
 const char* ktag_name(int tag);
 
 struct ParamView {
@@ -83,9 +84,13 @@ struct Engine {
   virtual int debug_copy(const char* what, float* dst, uint64_t max_floats, void* ws, int batch,
                          cudaStream_t st) = 0;
   virtual int debug_set(const char* key, long long value);
+  // valid time (unix seconds) of the state the next step starts from; only operators with time-dependent forcings use it
+  virtual int set_clock(double /*unix_seconds*/, cudaStream_t) { return 0; }
 };
 
 Engine* make_pangu_engine(const sky_pangu_config_t& cfg, int device);
 Engine* make_sfno_engine(const sky_sfno_config_t& cfg, int device);
+Engine* make_graphcast_engine(const sky_graphcast_config_t& cfg, int device);
+int toa_radiation_launch(float* out, int nlat, int nlon, double unix_seconds, cudaStream_t st);
 
 }  // namespace sky

@@ -35,9 +35,16 @@ __device__ __forceinline__ size_t img_offset(long long row, int col, int nkb) {
 struct AImage {
   const uint8_t* img0; const uint8_t* img1;
   int nkb0, nkb1;  // k-blocks per row tile in each image
+  // optional third / fourth part (GraphCast's mesh2grid node update: [v | e0 | e1 | e2]); nkb2 = nkb3 = 0 when unused
+  const uint8_t* img2 = nullptr; const uint8_t* img3 = nullptr;
+  int nkb2 = 0, nkb3 = 0;
   __device__ const uint8_t* kblock(int mt, int kb) const {
-    return kb < nkb0 ? img0 + ((size_t)mt * nkb0 + kb) * G2_A_BYTES
-                     : img1 + ((size_t)mt * nkb1 + (kb - nkb0)) * G2_A_BYTES;
+    if (kb < nkb0) return img0 + ((size_t)mt * nkb0 + kb) * G2_A_BYTES;
+    kb -= nkb0;
+    if (kb < nkb1 || nkb2 == 0) return img1 + ((size_t)mt * nkb1 + kb) * G2_A_BYTES;
+    kb -= nkb1;
+    if (kb < nkb2) return img2 + ((size_t)mt * nkb2 + kb) * G2_A_BYTES;
+    return img3 + ((size_t)mt * nkb3 + (kb - nkb2)) * G2_A_BYTES;
   }
 };
 

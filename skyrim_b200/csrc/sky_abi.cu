@@ -103,7 +103,8 @@ int Engine::range_scan(int slot, const void* img, size_t bytes, cudaStream_t st)
 
 const char* ktag_name(int t) {
   static const char* n[KT_COUNT] = {"embed", "qkv", "attn", "proj", "fc1", "fc2", "mlp", "down", "up", "recover", "copy",
-                                    "sfno_enc", "sfno_sht", "sfno_spec", "sfno_isht", "sfno_mlp", "sfno_dec", "sfno_misc"};
+                                    "sfno_enc", "sfno_sht", "sfno_spec", "sfno_isht", "sfno_mlp", "sfno_dec", "sfno_misc",
+                                    "gc_feat", "gc_hidden", "gc_ln", "gc_table", "gc_agg", "gc_out", "gc_misc"};
   return t >= 0 && t < KT_COUNT ? n[t] : "?";
 }
 
@@ -277,6 +278,9 @@ int sky_model_create(sky_model_t** out, int kind, const void* cfg, size_t cfg_by
   } else if (kind == SKY_MODEL_SFNO73) {
     if (cfg_bytes != sizeof(sky_sfno_config_t)) { set_error("bad config size"); return SKY_ERR_ARG; }
     e = make_sfno_engine(*static_cast<const sky_sfno_config_t*>(cfg), device);
+  } else if (kind == SKY_MODEL_GRAPHCAST) {
+    if (cfg_bytes != sizeof(sky_graphcast_config_t)) { set_error("bad config size"); return SKY_ERR_ARG; }
+    e = make_graphcast_engine(*static_cast<const sky_graphcast_config_t*>(cfg), device);
   } else {
     set_error("unknown model kind %d", kind);
     return SKY_ERR_ARG;
@@ -304,6 +308,22 @@ int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batc
   if (x_in == x_out) { set_error("x_in and x_out may not alias"); return SKY_ERR_ARG; }
   DeviceGuard guard(m->eng->device);
   return m->eng->step_cached(x_in, x_out, batch, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int sky_model_set_clock(sky_model_t* m, double unix_seconds, void* stream) {
+  if (!m) { set_error("null model"); return SKY_ERR_ARG; }
+  DeviceGuard guard(m->eng->device);
+  m->eng->drop_graphs();   // nothing in a captured step depends on the host value, but a new rollout starts clean
+  return m->eng->set_clock(unix_seconds, (cudaStream_t)stream);
+}
+
+int sky_toa_radiation(float* out, int32_t nlat, int32_t nlon, double unix_seconds, void* stream) {
+  if (!out || nlat < 2 || nlon < 1) { set_error("bad argument"); return SKY_ERR_ARG; }
+  cudaPointerAttributes attr;
+  SKY_CUDA_OK(cudaPointerGetAttributes(&attr, out));
+  if (attr.type != cudaMemoryTypeDevice) { set_error("out must be device memory"); return SKY_ERR_ARG; }
+  DeviceGuard guard(attr.device);
+  return toa_radiation_launch(out, nlat, nlon, unix_seconds, (cudaStream_t)stream);
 }
 
 int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* ws, int32_t batch,

@@ -11,7 +11,7 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _ffi
-from .config import PanguConfig, SFNOConfig
+from .config import GraphCastConfig, PanguConfig, SFNOConfig
 
 ARENA_ALIGN = 64  # floats (256 B)
 
@@ -49,10 +49,18 @@ def _sfno_cfg_c(cfg: SFNOConfig) -> _ffi.SFNOConfigC:
     return c
 
 
+def _graphcast_cfg_c(cfg: GraphCastConfig, graph) -> _ffi.GraphCastConfigC:
+    c = _ffi.GraphCastConfigC()
+    c.nlat, c.nlon, c.latent, c.layers = cfg.nlat, cfg.nlon, cfg.latent, cfg.layers
+    c.n_mesh, c.n_mesh_edges, c.n_g2m_edges = graph["n_mesh"], len(graph["mesh.senders"]), len(graph["g2m.senders"])
+    c.n_state, c.n_prog, c.n_static, c.dt_hours, c.ln_eps = cfg.n_state, cfg.n_prog, cfg.n_static, cfg.dt_hours, cfg.ln_eps
+    return c
+
+
 class StepEngine:
     """One 6-h step operator resident on one GPU."""
 
-    def __init__(self, cfg, device: int = 0, lib: str | None = None):
+    def __init__(self, cfg, device: int = 0, lib: str | None = None, graph=None):
         import torch
         if not torch.cuda.is_available():
             raise _ffi.SkyError("skyrim_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -64,6 +72,13 @@ class StepEngine:
             kind, cc = _ffi.SKY_MODEL_PANGU6, _pangu_cfg_c(cfg)
         elif isinstance(cfg, SFNOConfig):
             kind, cc = _ffi.SKY_MODEL_SFNO73, _sfno_cfg_c(cfg)
+        elif isinstance(cfg, GraphCastConfig):
+            # the multimesh and the grid<->mesh edge sets are built on the host once (icomesh.py) and travel in the arena
+            if graph is None:
+                from .icomesh import build_graph
+                graph = build_graph(cfg.nlat, cfg.nlon, cfg.mesh_levels, cfg.radius_frac)
+            self.graph = graph
+            kind, cc = _ffi.SKY_MODEL_GRAPHCAST, _graphcast_cfg_c(cfg, graph)
         else:
             raise TypeError(cfg)
         self.n_channels = cfg.n_channels
@@ -75,6 +90,9 @@ class StepEngine:
 
     # -- weights ---------------------------------------------------------------------------
     def load_weights(self, weights: "OrderedDict[str, np.ndarray]"):
+        if isinstance(self.cfg, GraphCastConfig) and not any(k.startswith("graph.") for k in weights):
+            from .icomesh import graph_arena_entries
+            weights = OrderedDict(list(weights.items()) + list(graph_arena_entries(self.graph).items()))
         arena, manifest = pack_arena(weights)
         self.load_arena(arena, manifest)
 
@@ -113,6 +131,23 @@ class StepEngine:
         _ffi.check(self._L.sky_model_step(self._h, x_in.data_ptr(), x_out.data_ptr(), B, ws.data_ptr(),
                                              ws.numel(), st), "sky_model_step", self._L)
         return x_out
+
+    def set_clock(self, when):
+        """Valid time of the LAST time slice of the state the next step starts from (datetime, numpy datetime64 or unix
+        seconds).  Only operators with time-dependent forcings (GraphCast) use it; they advance it themselves per step."""
+        t = unix_seconds(when)
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(self._L.sky_model_set_clock(self._h, t, st), "sky_model_set_clock", self._L)
+
+    def toa_radiation(self, when, out=None):
+        """(nlat, nlon) CUDA fp32: the toa-radiation forcing channel ("tp06") at time ``when``."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty((self.cfg.nlat, self.cfg.nlon), dtype=torch.float32, device=f"cuda:{self.device}")
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _ffi.check(self._L.sky_toa_radiation(out.data_ptr(), self.cfg.nlat, self.cfg.nlon, unix_seconds(when), st),
+                   "sky_toa_radiation", self._L)
+        return out
 
     def debug_tensor(self, what: str, shape, batch: int = 1):
         torch = self.torch
@@ -199,6 +234,20 @@ def perturb_ic(x, sigma_c, amp: float, seed: int, member0: int = 0):
     _ffi.check(_ffi.lib().sky_perturb_ic(x.data_ptr(), sigma_c.data_ptr(), float(amp), int(seed), int(member0), M,
                                          Cn, plane, st), "sky_perturb_ic")
     return x
+
+
+def unix_seconds(when) -> float:
+    """datetime (naive = UTC) / numpy datetime64 / number -> unix seconds"""
+    import datetime as _dt
+    if isinstance(when, (int, float)):
+        return float(when)
+    if isinstance(when, np.datetime64):
+        return float((when - np.datetime64("1970-01-01T00:00:00")) / np.timedelta64(1, "s"))
+    if isinstance(when, _dt.datetime):
+        if when.tzinfo is None:
+            when = when.replace(tzinfo=_dt.timezone.utc)
+        return when.timestamp()
+    raise TypeError(type(when))
 
 
 def launch_count() -> int:

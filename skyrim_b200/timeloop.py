@@ -16,7 +16,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .config import FCNV2_CHANNELS, PANGU_CHANNELS
+from .config import FCNV2_CHANNELS, GRAPHCAST_CHANNELS, PANGU_CHANNELS
 
 
 @dataclass
@@ -141,3 +141,64 @@ class PanguTimeLoop(_EngineTimeLoop):
 
 class SFNOTimeLoop(_EngineTimeLoop):
     channel_names = FCNV2_CHANNELS
+
+
+class GraphcastStepper:
+    """The stepper protocol the reference drives for GraphCast (/root/reference/skyrim/core/models/graphcast.py:102-118):
+    ``initialize(x, time) -> state`` and ``step(state) -> (state, output)`` with ``state = (time, fields, rng)``.
+    Upstream ``fields`` is an xarray Dataset with two time slices; here it is a CUDA tensor (B, 2, 83, nlat, nlon) holding
+    the same two slices in the reference's channel order (config.GRAPHCAST_CHANNELS), resident in HBM between steps."""
+
+    def __init__(self, loop):
+        self.loop = loop
+
+    def initialize(self, x, time):
+        torch = self.loop.torch
+        assert x.dim() == 5 and x.shape[1] == 2 and x.shape[2] == len(self.loop.channel_names), x.shape
+        fields = x.to(self.loop.device, dtype=torch.float32).contiguous()
+        self.loop.engine.set_clock(time)
+        return (time, fields, None)
+
+    def step(self, state):
+        time, fields, rng = state
+        eng, torch = self.loop.engine, self.loop.torch
+        B = fields.shape[0]
+        nxt = torch.empty_like(fields)
+        eng.step(fields.view(B, -1, *fields.shape[-2:]), nxt.view(B, -1, *fields.shape[-2:]))
+        time = time + self.loop.time_step
+        return (time, nxt, rng), nxt[:, -1]
+
+
+class GraphcastTimeLoop(_EngineTimeLoop):
+    """TimeLoop over the GraphCast engine: two history levels (t-6h, t); the first yield is the initial condition's last
+    slice, then one 6-h step per iteration.  The engine keeps the valid time on the device (time-dependent forcings)."""
+    n_history_levels = 2
+    channel_names = GRAPHCAST_CHANNELS
+
+    def __init__(self, engine):
+        super().__init__(engine)
+        self.stepper = GraphcastStepper(self)
+
+    def fill_forcing(self, x, time):
+        """write the toa-radiation forcing channel ("tp06") of both slices of an initial condition (B, 2, 83, H, W) in place"""
+        for k, dt in ((0, -self.time_step), (1, 0 * self.time_step)):
+            toa = self.engine.toa_radiation(time + dt)
+            x[:, k, -1] = toa
+        return x
+
+    def __call__(self, time, x, restart=None):
+        state = self.stepper.initialize(x, time)
+        yield time, state[1][:, -1].clone(), None
+        while True:
+            state, out = self.stepper.step(state)
+            yield state[0], out, None
+
+    def iter_host(self, time, x, n_steps: int):
+        for n, (t, out, _) in enumerate(self(time, x)):
+            yield t, out.cpu()
+            if n == n_steps:
+                return
+
+    def step_host(self, x_host):
+        """x_host: pinned (B, 2*83, H, W) -> pinned output of the same shape (bench.py e2e)"""
+        return super().step_host(x_host)

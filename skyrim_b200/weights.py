@@ -17,7 +17,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .config import PRESSURE_LEVELS, PanguConfig, SFNOConfig
+from .config import PRESSURE_LEVELS, GraphCastConfig, PanguConfig, SFNOConfig
 
 G0 = 9.80665
 
@@ -56,7 +56,7 @@ def channel_climatology(name: str):
     """(mean, std) of a channel by its reference name (e.g. 'z500', 't2m')."""
     surf = {"msl": (101325.0, 1200.0), "sp": (96500.0, 9000.0), "u10m": (0.0, 5.0),
             "v10m": (0.0, 5.0), "u100m": (0.0, 5.0), "v100m": (0.0, 5.0), "t2m": (280.0, 20.0),
-            "tcwv": (20.0, 15.0)}
+            "tcwv": (20.0, 15.0), "tp06": (1.2e6, 1.5e6)}   # "tp06" = toa incident solar radiation, J m^-2 per hour
     if name in surf:
         return surf[name]
     fam, p = name[0], int(name[1:])
@@ -72,6 +72,8 @@ def channel_climatology(name: str):
         return mu, 0.5 * mu
     if fam == "r":
         return 50.0, 25.0
+    if fam == "w":
+        return 0.0, 0.05 + 0.25 * (p / 1000.0)
     raise KeyError(name)
 
 
@@ -284,3 +286,81 @@ def sfno_tables(cfg: SFNOConfig) -> "OrderedDict[str, np.ndarray]":
         t[f"dft.fwd_{tag}"] = f.astype(np.float32)    # [(m, re/im), j]
         t[f"dft.inv_{tag}"] = i.astype(np.float32)    # [j, (m, re/im)]
     return t
+
+
+# ----------------------------------------------------------------------------------------
+# GraphCast
+# ----------------------------------------------------------------------------------------
+def graphcast_mlps(cfg: GraphCastConfig):
+    """(name, fan_in, fan_out, has_layernorm) of every MLP of the step, in execution order"""
+    L = cfg.latent
+    m = [("enc.grid_embed", cfg.n_features, L, True), ("enc.mesh_embed", 3, L, True), ("enc.g2m_edge_embed", 4, L, True),
+         ("enc.g2m_edge", 3 * L, L, True), ("enc.g2m_mesh", 2 * L, L, True), ("enc.g2m_grid", L, L, True),
+         ("proc.edge_embed", 4, L, True)]
+    for i in range(cfg.layers):
+        m += [(f"proc{i}.edge", 3 * L, L, True), (f"proc{i}.node", 2 * L, L, True)]
+    m += [("dec.m2g_edge_embed", 4, L, True), ("dec.m2g_edge", 3 * L, L, True), ("dec.m2g_grid", 2 * L, L, True),
+          ("dec.out", L, cfg.n_state, False)]
+    return m
+
+
+def graphcast_param_shapes(cfg: GraphCastConfig) -> "OrderedDict[str, tuple]":
+    L = cfg.latent
+    s = OrderedDict()
+    s["norm.mean"] = (cfg.n_state,)
+    s["norm.std"] = (cfg.n_state,)
+    s["norm.diff_std"] = (cfg.n_state,)
+    s["static.fields"] = (cfg.n_static, cfg.nlat, cfg.nlon)
+    for name, fi, fo, ln in graphcast_mlps(cfg):
+        s[name + ".w1"] = (L, fi)
+        s[name + ".b1"] = (L,)
+        s[name + ".w2"] = (fo, L)
+        s[name + ".b2"] = (fo,)
+        if ln:
+            s[name + ".ln.g"] = (fo,)
+            s[name + ".ln.b"] = (fo,)
+    return s
+
+
+def make_graphcast_weights(cfg: GraphCastConfig, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Synthetic GraphCast parameters (the JAX checkpoint is downloaded at run time by the reference,
+    /root/reference/skyrim/core/models/graphcast.py:51-54).  Linear layers are variance preserving; every MLP ends in a
+    LayerNorm, so the latents stay O(1) through the 16 processor layers."""
+    from .config import GRAPHCAST_CHANNELS
+    out = OrderedDict()
+    mu, sd = channel_stats(GRAPHCAST_CHANNELS)
+    for name, shape in graphcast_param_shapes(cfg).items():
+        if name == "norm.mean":
+            a = mu
+        elif name == "norm.std":
+            a = sd
+        elif name == "norm.diff_std":
+            a = (0.1 * sd).astype(np.float32)
+        elif name == "static.fields":
+            a = np.stack([2.0 * _smooth_field(seed, f"gc.static{i}", cfg.nlat, cfg.nlon) - 1.0 for i in range(shape[0])])
+        elif name.endswith("ln.g"):
+            g, b = _ln(seed, name[:-2], shape[0])
+            out[name], out[name[:-1] + "b"] = g, b
+            continue
+        elif name.endswith("ln.b"):
+            continue
+        elif name.endswith((".b1", ".b2")):
+            a = _tn(seed, name, shape, std=0.02)
+        else:
+            a = _tn(seed, name, shape, std=0.9 / np.sqrt(shape[-1]))
+        out[name] = np.ascontiguousarray(a, dtype=np.float32)
+    return OrderedDict((k, out[k]) for k in graphcast_param_shapes(cfg))
+
+
+def synthetic_graphcast_state(cfg: GraphCastConfig, seed: int = 0) -> np.ndarray:
+    """(2 * n_state, nlat, nlon): two time slices 6 h apart (the second = the first + a smooth tendency of 0.1 sigma).
+    The forcing channel of both slices is left at its climatological mean: the caller fills it with the toa radiation of
+    its own clock (engine: sky_toa_radiation; oracle: oracle.graphcast_ref.toa_radiation)."""
+    from .config import GRAPHCAST_CHANNELS
+    x0 = synthetic_state(GRAPHCAST_CHANNELS, cfg.nlat, cfg.nlon, seed)
+    x1 = synthetic_state(GRAPHCAST_CHANNELS, cfg.nlat, cfg.nlon, seed + 1000)
+    _, sd = channel_stats(GRAPHCAST_CHANNELS)
+    mu, _ = channel_stats(GRAPHCAST_CHANNELS)
+    x1 = x0 + np.float32(0.1) * (x1 - mu[:, None, None])
+    x0[-1], x1[-1] = mu[-1], mu[-1]
+    return np.concatenate([x0, x1], axis=0)
