@@ -102,3 +102,67 @@ def sfno_bytes(cfg: SFNOConfig) -> dict:
     b["sfno_mlp"] = 4.0 * E * 4 * ((L - 1) * P2 + P1)
     b["total"] = sum(b.values())
     return b
+
+
+def graphcast_counts(cfg, graph=None) -> dict:
+    """row counts of the GraphCast step; without a graph, the full-size counts of the refinement-6 mesh"""
+    if graph is not None:
+        return dict(Ng=cfg.n_grid, Nm=int(graph["n_mesh"]), Em=len(graph["mesh.senders"]), Eg=len(graph["g2m.senders"]))
+    assert (cfg.nlat, cfg.nlon, cfg.mesh_levels) == (721, 1440, 6)
+    return dict(Ng=cfg.n_grid, Nm=40962, Em=327660, Eg=1629780)
+
+
+def _graphcast_schedule(cfg, n):
+    """The engine's per-step GEMM schedule (csrc/graphcast_engine.cu::step) as (family, rows, K, N, bytes per row):
+    hidden GEMMs read their A operand image(s) (2 B per element) and write the 512-wide hidden image; LayerNorm GEMMs read
+    the hidden image and write / read-modify-write the residual stream (fp32) and the operand images listed."""
+    L, F = cfg.latent, 192
+    Ng, Nm, Em, Eg = n["Ng"], n["Nm"], n["Em"], n["Eg"]
+    s = []
+    # gathered per-node tables: a mesh-node table (<= 84 MB) stays in L2 and is counted once per GEMM; a grid-node table
+    # (1 GB) is read from HBM per gathered row
+    hid = lambda rows, K, grid_tab=0, mesh_tab=0: s.append(("gc_hidden", rows, K, L, 2.0 * K + 2.0 * L + grid_tab * 2.0 * L
+                                                            + mesh_tab * Nm * 2.0 * L / rows))
+    ln = lambda rows, rmw, img, yimg: s.append(("gc_ln", rows, L, L, 2.0 * L + (8.0 * L if rmw == 2 else 4.0 * L if rmw == 1 else 0.0)
+                                                + 2.0 * L * (img + yimg)))
+    tab = lambda rows, N: s.append(("gc_table", rows, L, N, 2.0 * L + 2.0 * N))
+    hid(Ng, F); ln(Ng, 1, 1, 0)                                   # grid embedding
+    tab(Ng, L); hid(Eg, L, grid_tab=1, mesh_tab=1); ln(Eg, 0, 0, 1)             # grid2mesh edges
+    hid(Nm, 2 * L); ln(Nm, 2, 1, 0)                               # mesh nodes
+    hid(Ng, L); ln(Ng, 2, 1, 0)                                   # grid nodes
+    for _ in range(cfg.layers):
+        tab(Nm, 2 * L); hid(Em, L, mesh_tab=2); ln(Em, 2, 1, 1); hid(Nm, 2 * L); ln(Nm, 2, 1, 0)
+    tab(Nm, L); tab(Ng, L); hid(3 * Ng, L, grid_tab=1, mesh_tab=1); ln(3 * Ng, 0, 0, 1)   # mesh2grid edges
+    hid(Ng, 4 * L); ln(Ng, 2, 1, 0)                               # grid update ([v | e0 | e1 | e2]: read as 4 images)
+    hid(Ng, L)                                                    # output head, first layer
+    return s
+
+
+def graphcast_flops(cfg, graph=None) -> dict:
+    """Dense FLOPs (2 MAC) of the step AS FORMULATED IN THE ENGINE — first layers split per input with per-node partial
+    products (the published concatenated form needs ~26 TFLOP, this one ~18.5) — except that the mesh2grid grid update is
+    counted with K = 2L (node + aggregated edges) although the engine contracts K = 4L (the three edge images separately)."""
+    n = graphcast_counts(cfg, graph)
+    f = dict(gc_hidden=0.0, gc_ln=0.0, gc_table=0.0, gc_feat=0.0, gc_agg=0.0)
+    for fam, rows, K, N, _ in _graphcast_schedule(cfg, n):
+        k_alg = 2 * cfg.latent if K == 4 * cfg.latent else (cfg.n_features if K == 192 else K)
+        f[fam] += 2.0 * rows * k_alg * N
+    f["gc_out"] = 2.0 * n["Ng"] * cfg.latent * cfg.n_state
+    f["total"] = sum(f.values())
+    return f
+
+
+def graphcast_bytes(cfg, graph=None) -> dict:
+    """Mandatory HBM bytes per step and kernel family for the engine's data flow (weights and the per-node tables are L2
+    resident at mesh size and are counted once per GEMM)."""
+    n = graphcast_counts(cfg, graph)
+    L = cfg.latent
+    b = dict(gc_hidden=0.0, gc_ln=0.0, gc_table=0.0)
+    for fam, rows, K, N, per_row in _graphcast_schedule(cfg, n):
+        b[fam] += rows * per_row
+    plane = 4.0 * n["Ng"]
+    b["gc_feat"] = plane * 2 * cfg.n_state + n["Ng"] * 192 * 2.0 + plane * (cfg.n_state + 1)    # state in; features, slice 0 and toa out
+    b["gc_agg"] = (n["Eg"] + cfg.layers * n["Em"]) * 2.0 * L + (1 + cfg.layers) * n["Nm"] * 2.0 * L
+    b["gc_out"] = n["Ng"] * 2.0 * L + plane * 2 * cfg.n_prog                                    # hidden in; x_t in, x_{t+1} out
+    b["total"] = sum(b.values())
+    return b

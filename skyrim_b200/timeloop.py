@@ -181,9 +181,10 @@ class GraphcastTimeLoop(_EngineTimeLoop):
 
     def fill_forcing(self, x, time):
         """write the toa-radiation forcing channel ("tp06") of both slices of an initial condition (B, 2, 83, H, W) in place"""
-        for k, dt in ((0, -self.time_step), (1, 0 * self.time_step)):
-            toa = self.engine.toa_radiation(time + dt)
-            x[:, k, -1] = toa
+        from .engine import unix_seconds
+        t = unix_seconds(time)
+        for k, dt in ((0, -self.time_step.total_seconds()), (1, 0.0)):
+            x[:, k, -1] = self.engine.toa_radiation(t + dt)
         return x
 
     def __call__(self, time, x, restart=None):

@@ -51,3 +51,23 @@ def compare_fullsize(y, fx) -> dict:
 
 def summarise(cmp: dict) -> dict:
     return {k: (float(np.max(v)) if k != "finite" else v) for k, v in cmp.items()}
+
+
+def compare_graphcast(y, x, diff_std, fx, cfg) -> dict:
+    """GraphCast full-size check.  y, x: (2 * n_state, 721, 1440) new / old state tensors; the fixture holds the oracle's
+    82 prognostic channels of the NEW slice (y_*) and the network's tendency (t_*, in units of diff_std).  Returns the
+    maxima over channels of the `compare_fullsize` metrics for the state and, as t_rel / t_block, for the tendency
+    (state = x + 0.1 sigma * tendency, so a 1e-3 state bound alone would tolerate a 1e-2 error of the network)."""
+    import torch
+    ns, npg = cfg.n_state, cfg.n_prog
+    y = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.asarray(y))
+    x = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.asarray(x))
+    new = y[ns:ns + npg]
+    s = summarise(compare_fullsize(new, fx))
+    ds = torch.from_numpy(np.asarray(diff_std, dtype=np.float32))[:npg].to(new.device)
+    tend = (new - x[ns:ns + npg].to(new.device)) / ds[:, None, None]
+    tfx = {"y_" + k[2:]: fx[k] for k in fx.files if k.startswith("t_")}
+    t = summarise(compare_fullsize(tend, tfx))
+    s.update(t_rel=t["rel"], t_block=t["block"], t_norm=t["norm"])
+    s["slice0_is_old_slice1"] = bool(torch.equal(y[:ns], x[ns:].to(y.device)))
+    return s
