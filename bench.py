@@ -13,6 +13,7 @@ is compared with the committed full-size oracle fixture (``verify``): a fast, fi
 
 The same invocation also measures (sub-records under ``configs``, skipped with ``--only-headline``):
   config 3  FourCastNet-v2 SFNO 6-h step on (73,721,1440)                     -> configs.sfno
+  config 4  GraphCast 6-h step on (2 x 83, 721, 1440), refinement-6 multimesh       -> configs.graphcast
   config 5  Pangu ensemble with 4 members per GPU (32 members on 8 GPUs)      -> configs.ensemble_m4
 each with ms/step, member-steps/s, per-family roofline fractions, fixture verification, and (N = 1) its e2e figure.
 One JSON line on rank 0.
@@ -34,6 +35,7 @@ METRIC = "6h rollout steps/sec on (69,721,1440); ensemble member-steps/sec @1/2/
 UNIT = "member-steps/s"
 VERIFY_TOL = 1e-3      # per-channel relative L2 on the point sample (north star); block means / RMS in sigma units below
 VERIFY_TOL_SIGMA = 5e-3
+VERIFY_TOL_TENDENCY = 2e-2   # GraphCast: per-channel relative L2 of the network tendency (state = x + 0.1 sigma x tendency)
 
 
 def _peaks():
@@ -236,6 +238,22 @@ def build_engine(model: str, d: Dist):
         if d.world > 1:
             shapes = sfno_param_shapes(cfg)
             shapes.update(sfno_table_shapes(cfg))
+    elif model == "graphcast":
+        from skyrim_b200.config import GRAPHCAST_CHANNELS as CH, graphcast_full
+        from skyrim_b200.icomesh import build_graph, graph_arena_entries
+        from skyrim_b200.timeloop import GraphcastTimeLoop as Loop
+        from skyrim_b200.weights import graphcast_param_shapes, make_graphcast_weights
+        cfg = graphcast_full()
+        graph = build_graph(cfg.nlat, cfg.nlon, cfg.mesh_levels, cfg.radius_frac)   # every rank: the table shapes size the arena
+        gent = graph_arena_entries(graph)
+        w = None
+        if d.rank == 0:
+            w = make_graphcast_weights(cfg, 0); w.update(gent)
+        shapes = None
+        if d.world > 1:
+            shapes = graphcast_param_shapes(cfg)
+            shapes.update({k: v.shape for k, v in gent.items()})
+        kw = {"graph": graph}
     else:
         from skyrim_b200.config import PANGU_CHANNELS as CH, pangu_full
         from skyrim_b200.timeloop import PanguTimeLoop as Loop
@@ -243,7 +261,7 @@ def build_engine(model: str, d: Dist):
         cfg = pangu_full()
         w = make_pangu_weights(cfg, 0) if d.rank == 0 else None
         shapes = pangu_param_shapes(cfg) if d.world > 1 else None
-    eng = StepEngine(cfg, d.local)
+    eng = StepEngine(cfg, d.local, **(kw if model == "graphcast" else {}))
     if d.world > 1:
         import torch.distributed as dist
         if d.rank == 0:
@@ -265,8 +283,8 @@ def family_roofline(model, cfg, M, fam_ms, peaks):
     """Per kernel family: algorithmic FLOPs and mandatory HBM bytes per step (skyrim_b200/roofline.py) over
     the family's measured device time per step -> achieved TFLOP/s, GB/s and the fraction of the bounding roofline."""
     from skyrim_b200 import roofline as R
-    fl = R.sfno_flops(cfg) if model == "sfno" else R.pangu_flops(cfg)
-    by = R.sfno_bytes(cfg) if model == "sfno" else R.pangu_bytes(cfg)
+    fl = R.sfno_flops(cfg) if model == "sfno" else R.graphcast_flops(cfg) if model == "graphcast" else R.pangu_flops(cfg)
+    by = R.sfno_bytes(cfg) if model == "sfno" else R.graphcast_bytes(cfg) if model == "graphcast" else R.pangu_bytes(cfg)
     out = {}
     for k, ms in fam_ms.items():
         f, b = M * fl.get(k, 0.0), M * by.get(k, 0.0)
@@ -289,8 +307,20 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
     dev = d.dev
     # ---- synthetic initial conditions: global member 0 is the unperturbed control (the fixture's IC), the others carry
     # the Philox perturbation keyed by their global member id (K11) ----
-    base = torch.from_numpy(synthetic_state(CH, cfg.nlat, cfg.nlon, 0))
-    x0 = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
+    gc = model == "graphcast"
+    GC_T0 = 1714521600.0   # valid time of the fixture's initial condition (second slice)
+    if gc:
+        from skyrim_b200.weights import synthetic_graphcast_state
+        assert M == 1, "GraphCast is benchmarked with one member per GPU (BASELINE config 4)"
+        base = torch.from_numpy(synthetic_graphcast_state(cfg, 0))
+        x0 = base.reshape(1, 2, cfg.n_state, cfg.nlat, cfg.nlon).to(dev)
+        loop.fill_forcing(x0, GC_T0)
+        x0 = x0.reshape(1, 2 * cfg.n_state, cfg.nlat, cfg.nlon).contiguous()
+        gc_diff_std = channel_stats(CH)[1] * 0.1
+    else:
+        base = torch.from_numpy(synthetic_state(CH, cfg.nlat, cfg.nlon, 0))
+        x0 = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
+    reset_clock = (lambda: eng.set_clock(GC_T0)) if gc else (lambda: None)   # every chain below restarts from the IC's time
     sigma = torch.from_numpy(channel_stats(CH)[1]).to(dev)
     first = 1 if d.rank == 0 else 0
     if M - first > 0:
@@ -299,6 +329,7 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
     y, z = torch.empty_like(x), torch.empty_like(x)
 
     # ---- warm-up on a copy + family breakdown (all families timed, outside the timed region) ----
+    reset_clock()
     for _ in range(max(warmup - 1, 0)):
         eng.step(x, y); x, y = y, x
     eng.profile_begin()
@@ -320,8 +351,8 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
         return src
 
     for _ in range(2):   # untimed: lets every (in, out) pair of the rotation reach its replay state
-        x.copy_(x0); chain(min(steps, 4))
-    x.copy_(x0)
+        x.copy_(x0); reset_clock(); chain(min(steps, 4))
+    x.copy_(x0); reset_clock()
     sampler = ClockSampler(d.local)
     launches0 = launch_count()
     d.barrier()
@@ -339,7 +370,7 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
 
     # ---- the same K steps once more with CUDA events around every launch of the dominant family (plain launches: the
     # per-launch events cannot live inside a replayed graph) -> roofline.achieved; its wall time is reported beside it ----
-    x.copy_(x0)
+    x.copy_(x0); reset_clock()
     d.barrier()
     eng.profile_begin([dominant])
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -352,7 +383,17 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
 
     # ---- verification of the timed run's first output against the full-size oracle fixture (rank 0, member 0) ----
     verify = None
-    if d.rank == 0:
+    if d.rank == 0 and gc:
+        from skyrim_b200.verify import compare_graphcast
+        s = compare_graphcast(z_first, x0[0], gc_diff_std, load_fixture(model), cfg)
+        ok = bool(s["finite"] and finite and s["rel"] < VERIFY_TOL and s["norm"] < VERIFY_TOL and s["block"] < VERIFY_TOL_SIGMA
+                  and s["t_rel"] < VERIFY_TOL_TENDENCY and s["slice0_is_old_slice1"])
+        verify = {"ok": ok, "against": f"tests/golden/{model}_721x1440_seed0.npz (one real oracle step)",
+                  "max_rel_err_per_channel": s["rel"], "max_rms_err_sigma": s["nrm"], "max_block_mean_err_sigma": s["block"],
+                  "max_norm_err": s["norm"], "tolerance": VERIFY_TOL, "rollout_finite": finite,
+                  "tendency_max_rel_err_per_channel": s["t_rel"], "tendency_max_block_mean_err_sigma": s["t_block"],
+                  "tendency_tolerance": VERIFY_TOL_TENDENCY}
+    elif d.rank == 0:
         s = summarise(compare_fullsize(z_first, load_fixture(model)))
         ok = bool(s["finite"] and finite and s["rel"] < VERIFY_TOL and s["norm"] < VERIFY_TOL and s["block"] < VERIFY_TOL_SIGMA)
         verify = {"ok": ok, "against": f"tests/golden/{model}_721x1440_seed0.npz (one real oracle step)",
@@ -365,6 +406,7 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
         xh = torch.empty((M,) + tuple(base.shape), dtype=torch.float32).pin_memory()
         xh.copy_(x0.cpu())
         e2e_steps = max(3, min(steps, 10))
+        reset_clock()
         out_h = loop.step_host(xh)  # warm-up (allocates the pinned result buffers)
         d.barrier()
         t0 = time.perf_counter()
@@ -375,7 +417,7 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
         # the rollout call as GlobalModel.rollout(save=True) drives it: IC uploaded once, EVERY state delivered to pinned
         # host memory, the copy of step n overlapping step n+1 (timeloop.iter_host) -- reported beside the strict number
         import datetime
-        for rep in range(2):    # first pass: ring allocation + graph capture of the three (in, out) pairs
+        for rep in range(0 if gc else 2):    # first pass: ring allocation + graph capture of the three (in, out) pairs
             it = loop.iter_host(datetime.datetime(2024, 1, 1), xh[:, None], e2e_steps + 2)
             next(it); next(it); next(it)
             t0 = time.perf_counter()
@@ -396,7 +438,7 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
         rec["e2e"] = {"value": d.world * M * 1000.0 / e2e_max, "unit": UNIT, "ms_per_step": e2e_max,
                       "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes,
                       "path": "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host",
-                      "rollout_every_state_to_host": {
+                      "rollout_every_state_to_host": None if roll_ms is None else {
                           "ms_per_step": roll_ms, "value": M * 1000.0 / roll_ms, "unit": UNIT, "d2h_bytes_per_step": sbytes,
                           "h2d_bytes_per_step": 0, "rank": d.rank,
                           "path": "TimeLoop.iter_host (what GlobalModel.rollout(save=True) drives): IC uploaded once, every "
@@ -441,6 +483,8 @@ def run_ours(args):
         k = max(3, min(args.steps, 8))
         if args.model != "sfno":
             subs["sfno"] = bench_model("sfno", 1, k, 3, d, e2e=(d.world == 1))
+        if args.model != "graphcast":   # BASELINE config 4: GraphCast 6-h step on the 0.25 deg grid, one member per GPU
+            subs["graphcast"] = bench_model("graphcast", 1, k, 3, d, e2e=(d.world == 1))
         if args.model == "pangu" and M != 4:
             subs["ensemble_m4"] = bench_model("pangu", 4, k, 3, d, e2e=False)
     cb = None
@@ -467,10 +511,13 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": ("f16 hi+lo split operands / f32 accumulate (tcgen05 kind::f16), f32 state" if sfno else
+                      "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, residual streams, LayerNorm" if args.model == "graphcast" else
                       "f16 operands / f32 accumulate (tcgen05 kind::f16), f32 state, LN, softmax"),
             "data": "synthetic",
             "config": {"workload": ("FourCastNet-v2 SFNO rollout (chained 6-h steps), synthetic (73,721,1440) IC, state resident in HBM"
                                     if sfno else
+                                    "GraphCast rollout (chained 6-h steps), synthetic (2 x 83,721,1440) IC, refinement-6 multimesh, state resident in HBM"
+                                    if args.model == "graphcast" else
                                     "Pangu 7-day rollout (chained 6-h steps), synthetic (69,721,1440) IC, state resident in HBM"),
                        "members_per_gpu": M, "members_total": d.world * M,
                        "l2": "inputs larger than L2 (state 0.3 GB + >2 GB activations streamed per step)",
@@ -511,7 +558,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members-per-gpu", type=int, default=1)
-    ap.add_argument("--model", default="pangu", choices=["pangu", "sfno"],
+    ap.add_argument("--model", default="pangu", choices=["pangu", "sfno", "graphcast"],
                     help="headline workload: pangu (default) or sfno (FourCastNet-v2 73-channel rollout)")
     ap.add_argument("--only-headline", action="store_true", help="skip the configs.sfno / configs.ensemble_m4 sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")

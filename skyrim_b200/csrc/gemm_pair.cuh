@@ -21,13 +21,14 @@
 
 namespace sky {
 
-template <int C>
+template <int C, int NT_ = 192>
 struct GPairCfg {
   static constexpr int NKB = C / 64;
-  static constexpr int NT = 192;                 // n-tile = one MMA N
+  static constexpr int NT = NT_;                 // n-tile = one MMA N (192: Pangu QKV; 256: GraphCast hidden layers, K = 512)
   static constexpr int W_FULL = NT * 128;        // one (n-tile, k-block) item of the weight image
-  static constexpr int W_HALF = W_FULL / 2;      // this CTA's 96 rows of it
-  static constexpr int S = C == 192 ? 10 : 7;
+  static constexpr int W_HALF = W_FULL / 2;      // this CTA's NT / 2 rows of it
+  static constexpr int S = C == 192 ? 10 : C == 384 ? 7 : 4;
+  static_assert(2 * NT <= 512 && NT % 16 == 0 && NT <= 256, "two accumulators in TMEM, one UMMA N");
   static constexpr int A_BYTES = NKB * G2_A_BYTES;
   static constexpr int OFF_W = A_BYTES;
   static constexpr int OFF_PATCH = OFF_W + S * W_HALF;
@@ -38,13 +39,13 @@ struct GPairCfg {
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
-template <class Epi, int C>
+template <class Epi, int C, int NT_ = 192>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 k_gemm_pair(const uint8_t* __restrict__ Aimg,   // fp16 tile image of A (tokens, C)
             const Epi epi,
             const uint8_t* __restrict__ Wimg,   // [N/192][C/64][192 x 128B]
             long long M, int num_m_tiles, int num_n_tiles, int expflags) {
-  using Cfg = GPairCfg<C>;
+  using Cfg = GPairCfg<C, NT_>;
   extern __shared__ __align__(1024) uint8_t smem_gp[];
   uint8_t* smem = smem_gp;
   uint8_t* a_s = smem;
@@ -195,11 +196,11 @@ k_gemm_pair(const uint8_t* __restrict__ Aimg,   // fp16 tile image of A (tokens,
   }
 }
 
-template <class Epi, int C>
+template <class Epi, int C, int NT_ = 192>
 int launch_gemm_pair(const uint8_t* Aimg, const Epi& epi, const uint8_t* Wimg, long long M, int N, int num_sms,
                      cudaStream_t st) {
-  using Cfg = GPairCfg<C>;
-  auto kern = k_gemm_pair<Epi, C>;
+  using Cfg = GPairCfg<C, NT_>;
+  auto kern = k_gemm_pair<Epi, C, NT_>;
   static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
   if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);

@@ -21,6 +21,7 @@
 
 #include "engine.h"
 #include "graphcast_ops.cuh"
+#include "gemm_pair.cuh"
 
 namespace sky {
 
@@ -45,12 +46,17 @@ struct GraphCastEngine : Engine {
   std::vector<WImg> proc_wsr;           // (N = 1024: [W1s; W1r], K = 512)
   const float *mean = nullptr, *stdv = nullptr, *dstd = nullptr, *statics = nullptr, *zero_bias = nullptr;
   // graph
-  int *mesh_s = nullptr, *mesh_r = nullptr, *mesh_ptr = nullptr, *g2m_s = nullptr, *g2m_r = nullptr, *g2m_ptr = nullptr,
-      *m2g_s = nullptr, *m2g_r = nullptr;
+  int *mesh_s = nullptr, *mesh_r = nullptr, *g2m_s = nullptr, *g2m_r = nullptr, *m2g_s = nullptr, *m2g_r = nullptr;
+  struct SegPlan {   // chunked CSR reduction (k_gc_segsum): chunk table, cut nodes, fp32 partial rows
+    GcSegChunk* chunks = nullptr; int n_chunks = 0;
+    GcSegMulti* multi = nullptr; int n_multi = 0;
+    float* partial = nullptr;
+  } mesh_seg, g2m_seg;
   // input-independent embeddings
   uint8_t *e_g2m_img = nullptr, *e_m2g_img = nullptr, *e_mesh_img = nullptr, *vm0_img = nullptr;
   float *e_mesh_f32 = nullptr, *vm0_f32 = nullptr;
   __half* g2m_tr = nullptr;             // (Nm, 512): embedded mesh nodes x W1r(g2m_edge)^T
+  bool use_pair = true;   // debug_set("gc_pair", 0): hidden GEMMs on k_gemm2 (A/B timing, bisection)
   // clock
   double* clock_dev = nullptr;
   GcClock* clk_dev = nullptr;
@@ -119,6 +125,39 @@ struct GraphCastEngine : Engine {
     }
     return 0;
   }
+  // receiver-sorted edge list -> chunk table (segments cut at GC_SEG_CHUNK edges).  Built on the host from the CSR pointer.
+  int load_segplan(SegPlan& sp, const char* ptr_name, long long n_nodes, cudaStream_t st) {
+    const float* src = param(ptr_name, (uint64_t)n_nodes + 1);
+    if (!src) return SKY_ERR_ARG;
+    std::vector<float> hp((size_t)n_nodes + 1);
+    SKY_CUDA_OK(cudaMemcpyAsync(hp.data(), src, hp.size() * 4, cudaMemcpyDeviceToHost, st));
+    SKY_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<GcSegChunk> ck;
+    std::vector<GcSegMulti> mu;
+    int parts = 0;
+    for (long long n = 0; n < n_nodes; ++n) {
+      const int e0 = (int)hp[n], e1 = (int)hp[n + 1];
+      const int nc = e1 - e0 <= GC_SEG_CHUNK ? 1 : (e1 - e0 + GC_SEG_CHUNK - 1) / GC_SEG_CHUNK;
+      if (nc == 1) { ck.push_back(GcSegChunk{(int)n, e0, e1, -1}); continue; }
+      mu.push_back(GcSegMulti{(int)n, parts, parts + nc});
+      for (int c = 0; c < nc; ++c) {
+        const int a = e0 + c * GC_SEG_CHUNK;
+        ck.push_back(GcSegChunk{(int)n, a, a + GC_SEG_CHUNK < e1 ? a + GC_SEG_CHUNK : e1, parts++});
+      }
+    }
+    sp.n_chunks = (int)ck.size(); sp.n_multi = (int)mu.size();
+    sp.chunks = dalloc<GcSegChunk>(ck.size());
+    if (!sp.chunks) return SKY_ERR_NOMEM;
+    SKY_CUDA_OK(cudaMemcpyAsync(sp.chunks, ck.data(), ck.size() * sizeof(GcSegChunk), cudaMemcpyHostToDevice, st));
+    if (sp.n_multi) {
+      sp.multi = dalloc<GcSegMulti>(mu.size());
+      sp.partial = dalloc<float>((size_t)parts * GC_L);
+      if (!sp.multi || !sp.partial) return SKY_ERR_NOMEM;
+      SKY_CUDA_OK(cudaMemcpyAsync(sp.multi, mu.data(), mu.size() * sizeof(GcSegMulti), cudaMemcpyHostToDevice, st));
+    }
+    SKY_CUDA_OK(cudaStreamSynchronize(st));   // the host vectors die here
+    return 0;
+  }
   int load_index(int*& dst, const char* name, long long n, cudaStream_t st) {
     const float* src = param(name, (uint64_t)n);
     if (!src) return SKY_ERR_ARG;
@@ -142,7 +181,14 @@ struct GraphCastEngine : Engine {
     epi.out = out; epi.bias = b1; epi.ta = ta; epi.lda = lda; epi.ia = ia; epi.tb = tb; epi.ldb = ldb; epi.ib = ib;
     prof_begin(tag, st);
     count_launch();
-    const int rc = launch_gemm2<EpiGcSiluImg<kG>, 256, 8>(A, epi, w.img, M, GC_L, Kp, num_sms, st);
+    int rc;
+    if (Kp == GC_L && A.nkb0 == GC_NKB && use_pair)
+      // K = 512 from one operand image (edge updates, grid2mesh grid update, output head): A-stationary CTA pairs,
+      // cta_group::2 M = 256 — each CTA keeps its 128 x 512 A tile for both n-tiles and streams half of every weight item
+      // (k_gemm2 moves 768 KB of L2 -> SM traffic per 128 rows here, the pair 384 KB)
+      rc = launch_gemm_pair<EpiGcSiluImg<kG>, GC_L, 256>(A.img0, epi, w.img, M, GC_L, num_sms, st);
+    else
+      rc = launch_gemm2<EpiGcSiluImg<kG>, 256, 8>(A, epi, w.img, M, GC_L, Kp, num_sms, st);
     prof_end(tag, st);
     return rc;
   }
@@ -165,11 +211,17 @@ struct GraphCastEngine : Engine {
     prof_end(tag, st);
     return rc;
   }
-  int segsum(int tag, const uint8_t* yimg, const int* ptr, long long n_nodes, uint8_t* out, cudaStream_t st) {
+  int segsum(int tag, const uint8_t* yimg, const SegPlan& sp, uint8_t* out, cudaStream_t st) {
     prof_begin(tag, st);
     count_launch();
-    k_gc_segsum<<<(unsigned)((n_nodes * 32 + 255) / 256), 256, 0, st>>>(yimg, ptr, (int)n_nodes, out);
+    k_gc_segsum<<<(unsigned)(((long long)sp.n_chunks * 32 + 255) / 256), 256, 0, st>>>(yimg, sp.chunks, sp.n_chunks, out, sp.partial);
     prof_end(tag, st);
+    if (sp.n_multi) {
+      prof_begin(tag, st);
+      count_launch();
+      k_gc_segsum_fin<<<(unsigned)(((long long)sp.n_multi * 32 + 255) / 256), 256, 0, st>>>(sp.partial, sp.multi, sp.n_multi, out);
+      prof_end(tag, st);
+    }
     SKY_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -208,10 +260,10 @@ struct GraphCastEngine : Engine {
     // ---- graph tables
     if ((rc = load_index(mesh_s, "graph.mesh.senders", Em, st))) return rc;
     if ((rc = load_index(mesh_r, "graph.mesh.receivers", Em, st))) return rc;
-    if ((rc = load_index(mesh_ptr, "graph.mesh.ptr", Nm + 1, st))) return rc;
+    if ((rc = load_segplan(mesh_seg, "graph.mesh.ptr", Nm, st))) return rc;
     if ((rc = load_index(g2m_s, "graph.g2m.senders", Eg, st))) return rc;
     if ((rc = load_index(g2m_r, "graph.g2m.receivers", Eg, st))) return rc;
-    if ((rc = load_index(g2m_ptr, "graph.g2m.ptr", Nm + 1, st))) return rc;
+    if ((rc = load_segplan(g2m_seg, "graph.g2m.ptr", Nm, st))) return rc;
     {
       const float* s = param("graph.m2g.senders", (uint64_t)3 * Ng);
       if (!s) return SKY_ERR_ARG;
@@ -354,7 +406,7 @@ struct GraphCastEngine : Engine {
       if ((rc = table(KT_GC_TABLE, w.vg_img, g2m_ws, Ng, w.tg, st))) return rc;
       if ((rc = hidden<2>(KT_GC_HIDDEN, A1(e_g2m_img, GC_NKB), L, g2m_edge.w1, g2m_edge.b1, Eg, w.hid, w.tg, L, g2m_s, g2m_tr, L, g2m_r, st))) return rc;
       if ((rc = ln_gemm(KT_GC_LN, w.hid, g2m_edge, Eg, nullptr, nullptr, nullptr, w.yimg, st))) return rc;
-      if ((rc = segsum(KT_GC_AGG, w.yimg, g2m_ptr, Nm, w.agg_img, st))) return rc;
+      if ((rc = segsum(KT_GC_AGG, w.yimg, g2m_seg, w.agg_img, st))) return rc;
       if ((rc = hidden<0>(KT_GC_HIDDEN, A2(vm0_img, w.agg_img), 2 * L, g2m_mesh.w1, g2m_mesh.b1, Nm, w.hid_m, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
       if ((rc = ln_gemm(KT_GC_LN, w.hid_m, g2m_mesh, Nm, vm0_f32, w.vm, w.vm_img, nullptr, st))) return rc;
       if ((rc = hidden<0>(KT_GC_HIDDEN, A1(w.vg_img, GC_NKB), L, g2m_grid.w1, g2m_grid.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
@@ -369,7 +421,7 @@ struct GraphCastEngine : Engine {
         if ((rc = hidden<2>(KT_GC_HIDDEN, A1(em_in_img, GC_NKB), L, proc_edge[i].w1, proc_edge[i].b1, Em, w.hid_m, w.tm, 2 * L, mesh_s, w.tm + L,
                             2 * L, mesh_r, st))) return rc;
         if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_edge[i], Em, em_in, w.em, w.em_img, w.ym_img, st))) return rc;
-        if ((rc = segsum(KT_GC_AGG, w.ym_img, mesh_ptr, Nm, w.agg_img, st))) return rc;
+        if ((rc = segsum(KT_GC_AGG, w.ym_img, mesh_seg, w.agg_img, st))) return rc;
         if ((rc = hidden<0>(KT_GC_HIDDEN, A2(w.vm_img, w.agg_img), 2 * L, proc_node[i].w1, proc_node[i].b1, Nm, w.hid_m, nullptr, 0, nullptr, nullptr, 0,
                             nullptr, st))) return rc;
         if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_node[i], Nm, w.vm, w.vm, w.vm_img, nullptr, st))) return rc;
@@ -406,6 +458,11 @@ struct GraphCastEngine : Engine {
     }
     SKY_CUDA_OK(cudaGetLastError());
     return 0;
+  }
+
+  int debug_set(const char* key, long long value) override {
+    if (!strcmp(key, "gc_pair")) { use_pair = value != 0; drop_graphs(); return 0; }
+    return Engine::debug_set(key, value);
   }
 
   int debug_copy(const char* what, float* dst, uint64_t max_floats, void* ws_base, int, cudaStream_t st) override {

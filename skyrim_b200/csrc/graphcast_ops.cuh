@@ -375,11 +375,18 @@ __global__ void __launch_bounds__(128) k_gc_features(const float* __restrict__ x
   __half* my = tile[threadIdx.x];
   int f = 0;
   if (ok) {
+    // eight independent plane reads in flight per thread (16 warps per SM: latency has to be covered by the thread itself)
     for (int s = 0; s < 2; ++s)
-      for (int ch = 0; ch < nprog; ++ch) {
-        const float v = __ldg(xin + (size_t)(s * nstate + ch) * plane + g);
-        my[f++] = __float2half_rn((v - __ldg(mean + ch)) / __ldg(stdv + ch));
-        if (s == 1) xout[(size_t)ch * plane + g] = v;
+      for (int c0 = 0; c0 < nprog; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = c0 + j < nprog ? __ldg(xin + (size_t)(s * nstate + c0 + j) * plane + g) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < nprog) {
+            my[f++] = __float2half_rn((v[j] - __ldg(mean + c0 + j)) / __ldg(stdv + c0 + j));
+            if (s == 1) xout[(size_t)(c0 + j) * plane + g] = v[j];
+          }
       }
     // prognostic channels of slice 0 of the next state come from slice 1 (written above); slice 0 itself is dropped
     const int la = (int)(g / nlon), lo = (int)(g % nlon);
@@ -425,37 +432,76 @@ __global__ void __launch_bounds__(128) k_gc_features(const float* __restrict__ x
   }
 }
 
-// agg[n] = sum over the incoming edges [ptr[n], ptr[n+1]) of the y image rows (fp32 accumulation in edge order:
-// deterministic) -> fp16 tile image.  One warp per node, a lane owns two 16-byte chunks of the 64 per row.
-__global__ void __launch_bounds__(256) k_gc_segsum(const uint8_t* __restrict__ yimg, const int* __restrict__ ptr, int n_nodes,
-                                                   uint8_t* __restrict__ out) {
-  const int node = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+// agg[n] = sum over the incoming edges [ptr[n], ptr[n+1]) of the y image rows -> fp16 tile image; fp32 accumulation in a
+// FIXED order (deterministic, no atomics).  The receiver degrees are very uneven (grid2mesh at 0.25 deg: median 29, the
+// mesh nodes at the poles 4320), so the segments are cut into chunks of <= GC_SEG_CHUNK edges (table built at load):
+// one warp per chunk, a lane owns two 16-byte chunks of the 64 per row, four edges in flight.  A node with a single chunk
+// is finished here; the others leave fp32 partial rows that k_gc_segsum_fin adds in chunk order.
+constexpr int GC_SEG_CHUNK = 64;
+struct GcSegChunk { int node, e0, e1, part; };   // part < 0: single-chunk node; else row of the partial buffer
+
+__device__ __forceinline__ uint4 gc_img_ld(const uint8_t* img, int row, int j) {
+  return __ldg(reinterpret_cast<const uint4*>(img + (size_t)(row >> 7) * GC_NKB * G2_A_BYTES + (size_t)(j >> 3) * G2_A_BYTES +
+                                              sw128_offset((uint32_t)(row & 127), (uint32_t)(j & 7))));
+}
+__device__ __forceinline__ void gc_img_st(uint8_t* img, int row, int j, const float* a) {
+  uint4 pk;
+  pk.x = pack_half2(a[0], a[1]); pk.y = pack_half2(a[2], a[3]); pk.z = pack_half2(a[4], a[5]); pk.w = pack_half2(a[6], a[7]);
+  *reinterpret_cast<uint4*>(img + (size_t)(row >> 7) * GC_NKB * G2_A_BYTES + (size_t)(j >> 3) * G2_A_BYTES +
+                            sw128_offset((uint32_t)(row & 127), (uint32_t)(j & 7))) = pk;
+}
+__global__ void __launch_bounds__(256) k_gc_segsum(const uint8_t* __restrict__ yimg, const GcSegChunk* __restrict__ chunks, int n_chunks,
+                                                   uint8_t* __restrict__ out, float* __restrict__ partial) {
+  const int ci = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (node >= n_nodes) return;
-  const int e0 = __ldg(ptr + node), e1 = __ldg(ptr + node + 1);
+  if (ci >= n_chunks) return;
+  const GcSegChunk c = chunks[ci];
   float a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a[i] = 0.f;
-  for (int e = e0; e < e1; ++e) {
-    const uint8_t* rowbase = yimg + (size_t)(e >> 7) * GC_NKB * G2_A_BYTES;
-    const uint32_t r = (uint32_t)(e & 127);
+  int e = c.e0;
+  for (; e + 4 <= c.e1; e += 4) {
+    uint4 p[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { p[2 * u] = gc_img_ld(yimg, e + u, lane); p[2 * u + 1] = gc_img_ld(yimg, e + u, lane + 32); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { add_h8(a, p[2 * u]); add_h8(a + 8, p[2 * u + 1]); }
+  }
+  for (; e < c.e1; ++e) { add_h8(a, gc_img_ld(yimg, e, lane)); add_h8(a + 8, gc_img_ld(yimg, e, lane + 32)); }
+  if (c.part < 0) {
+    gc_img_st(out, c.node, lane, a);
+    gc_img_st(out, c.node, lane + 32, a + 8);
+  } else {
+    float* d = partial + (size_t)c.part * GC_L;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;   // chunk 0..63: k-block j / 8, chunk j % 8
-      const uint4 p = __ldg(reinterpret_cast<const uint4*>(rowbase + (size_t)(j >> 3) * G2_A_BYTES + sw128_offset(r, (uint32_t)(j & 7))));
-      add_h8(a + 8 * h, p);
+      *reinterpret_cast<float4*>(d + (lane + 32 * h) * 8) = make_float4(a[8 * h], a[8 * h + 1], a[8 * h + 2], a[8 * h + 3]);
+      *reinterpret_cast<float4*>(d + (lane + 32 * h) * 8 + 4) = make_float4(a[8 * h + 4], a[8 * h + 5], a[8 * h + 6], a[8 * h + 7]);
     }
   }
-  uint8_t* obase = out + (size_t)(node >> 7) * GC_NKB * G2_A_BYTES;
-  const uint32_t r = (uint32_t)(node & 127);
+}
+struct GcSegMulti { int node, p0, p1; };   // a node whose segment was cut: partial rows [p0, p1)
+__global__ void __launch_bounds__(256) k_gc_segsum_fin(const float* __restrict__ partial, const GcSegMulti* __restrict__ multi, int n_multi,
+                                                       uint8_t* __restrict__ out) {
+  const int mi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (mi >= n_multi) return;
+  const GcSegMulti m = multi[mi];
+  float a[16];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int j = lane + 32 * h;
-    uint4 pk;
-    pk.x = pack_half2(a[8 * h], a[8 * h + 1]); pk.y = pack_half2(a[8 * h + 2], a[8 * h + 3]);
-    pk.z = pack_half2(a[8 * h + 4], a[8 * h + 5]); pk.w = pack_half2(a[8 * h + 6], a[8 * h + 7]);
-    *reinterpret_cast<uint4*>(obase + (size_t)(j >> 3) * G2_A_BYTES + sw128_offset(r, (uint32_t)(j & 7))) = pk;
+  for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  for (int p = m.p0; p < m.p1; ++p) {
+    const float* s = partial + (size_t)p * GC_L;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(s + (lane + 32 * h) * 8));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(s + (lane + 32 * h) * 8 + 4));
+      a[8 * h] += u.x; a[8 * h + 1] += u.y; a[8 * h + 2] += u.z; a[8 * h + 3] += u.w;
+      a[8 * h + 4] += v.x; a[8 * h + 5] += v.y; a[8 * h + 6] += v.z; a[8 * h + 7] += v.w;
+    }
   }
+  gc_img_st(out, m.node, lane, a);
+  gc_img_st(out, m.node, lane + 32, a + 8);
 }
 
 }  // namespace sky

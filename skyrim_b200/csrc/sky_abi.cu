@@ -313,7 +313,7 @@ int sky_model_step(sky_model_t* m, const float* x_in, float* x_out, int32_t batc
 int sky_model_set_clock(sky_model_t* m, double unix_seconds, void* stream) {
   if (!m) { set_error("null model"); return SKY_ERR_ARG; }
   DeviceGuard guard(m->eng->device);
-  m->eng->drop_graphs();   // nothing in a captured step depends on the host value, but a new rollout starts clean
+  // captured steps stay valid: the clock lives in device memory, nothing in a graph depends on the host value
   return m->eng->set_clock(unix_seconds, (cudaStream_t)stream);
 }
 

@@ -86,6 +86,38 @@ def test_sfno_full_size_oracle_parity():
     assert s["nrm"] < TOL_SIGMA and s["block"] < TOL_SIGMA and s["last"] < 4 * TOL_SIGMA, s
 
 
+def test_graphcast_full_size_oracle_parity():
+    """BASELINE config 4's step: GraphCast on the 0.25 deg grid with the refinement-6 multimesh (40,962 nodes, 327,660 mesh
+    edges, 1.63 M grid2mesh and 3.11 M mesh2grid edges, 16 layers) against ONE real oracle step (135 s on 8 host threads),
+    for the stepped state (north-star tolerance) and for the network's tendency itself."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from skyrim_b200.config import graphcast_full
+    from skyrim_b200.engine import StepEngine
+    from skyrim_b200.timeloop import GraphcastTimeLoop
+    from skyrim_b200.verify import compare_graphcast, load_fixture
+    from skyrim_b200.weights import make_graphcast_weights, synthetic_graphcast_state
+    cfg = graphcast_full()
+    w = make_graphcast_weights(cfg, 0)
+    eng = StepEngine(cfg, 0)
+    eng.load_weights(w)
+    fx = load_fixture("graphcast")
+    t0 = float(fx["t0"])
+    x = torch.from_numpy(synthetic_graphcast_state(cfg, 0)).reshape(1, 2, cfg.n_state, cfg.nlat, cfg.nlon).cuda()
+    GraphcastTimeLoop(eng).fill_forcing(x, t0)
+    x = x.reshape(1, 2 * cfg.n_state, cfg.nlat, cfg.nlon).contiguous()
+    assert np.allclose(x[0, :, ::64, ::64].cpu().numpy(), fx["x0_sample"], rtol=2e-5, atol=0), "seeded IC (incl. toa forcing) differs from the fixture's"
+    eng.set_clock(t0)
+    y = eng.step(x)
+    s = compare_graphcast(y[0], x[0], w["norm.diff_std"], fx, cfg)
+    print(f"\n[graphcast 721x1440 vs oracle fixture] state: rel {s['rel']:.3e} nrm {s['nrm']:.3e} block {s['block']:.3e} last {s['last']:.3e} "
+          f"norm {s['norm']:.3e}; tendency: rel {s['t_rel']:.3e} block {s['t_block']:.3e} norm {s['t_norm']:.3e}")
+    assert s["finite"] and s["slice0_is_old_slice1"]
+    assert s["rel"] < TOL and s["norm"] < TOL and s["nrm"] < TOL_SIGMA and s["block"] < TOL_SIGMA and s["last"] < TOL_SIGMA
+    assert s["t_rel"] < 2e-2 and s["t_norm"] < 5e-3, "tendency (network output) error"
+    eng.close()
+
+
 @pytest.mark.parametrize("nlat,nlon", [(181, 480), (121, 384)])
 def test_pangu_mid_size_parity_more_tiles_than_sms(nlat, nlon):
     """181x480: 43,200 / 10,800 tokens = 338 / 85 row tiles, 1,014 QKV tiles, 169 MLP super-tile pairs on 148 SMs

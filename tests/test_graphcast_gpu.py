@@ -154,3 +154,17 @@ def test_skyrim_api_graphcast():
     assert np.allclose(da.values[2], pred.prediction.values[1], rtol=0, atol=0)
     one = model.model.predict_one_step(datetime.datetime(2024, 4, 4, 0, 0))
     assert np.array_equal(one.values[1], da.values[1])
+
+
+def test_pair_hidden_gemm_matches_single_cta_kernel():
+    """K = 512 hidden layers run on CTA pairs (k_gemm_pair<.., 512, 256>); the single-CTA k_gemm2 path must give the
+    same bits (same K order, same epilogue functor)"""
+    cfg, graph, w, x, eng = _setup(49, 120, 3, 2)
+    xs = torch.from_numpy(x)[None].cuda()
+    eng.set_clock(T0)
+    a = eng.step(xs).clone()
+    eng.debug_set("gc_pair", 0)
+    eng.set_clock(T0)
+    b = eng.step(xs)
+    assert torch.equal(a, b)
+    eng.close()
