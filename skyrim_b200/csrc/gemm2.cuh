@@ -84,6 +84,11 @@ struct EpiCtx {
   // per-row-group scratch an epilogue may cache across the n-tiles of one m-tile (EpiQkvWin: destination row of this lane)
   mutable long long aux_row0 = -1;
   mutable int aux = 0;
+  // row-statistics exchange with the peer CTA of a column-split pair (gemm_split.cuh); x_own_bar == nullptr elsewhere
+  uint64_t* x_own_bar = nullptr;   // completes when the peer's 32 (sum, sum of squares) pairs of this lane quarter landed
+  uint32_t x_own_stat = 0;         // shared-space address of this CTA's slot: 32 x {float s, ss}
+  uint32_t x_peer_stat = 0, x_peer_bar = 0;   // shared::cluster addresses of the same slot / barrier in the peer CTA
+  uint32_t x_parity = 0;
 };
 
 struct AccTmem2 {

@@ -22,6 +22,7 @@
 #include "engine.h"
 #include "graphcast_ops.cuh"
 #include "gemm_pair.cuh"
+#include "gemm_split.cuh"
 
 namespace sky {
 
@@ -31,6 +32,7 @@ static inline size_t img_bytes(long long rows, int nkb) { return (size_t)(pad128
 struct WImg { uint8_t* img = nullptr; int N = 0, Kp = 0, BN = 0; };
 struct Mlp {
   WImg w1, w2;
+  WImg w2s;   // second layer packed in 256-row halves for the column-split pair kernel (k_gemm_split)
   const float *b1 = nullptr, *b2 = nullptr, *g = nullptr, *be = nullptr;
 };
 
@@ -57,6 +59,7 @@ struct GraphCastEngine : Engine {
   float *e_mesh_f32 = nullptr, *vm0_f32 = nullptr;
   __half* g2m_tr = nullptr;             // (Nm, 512): embedded mesh nodes x W1r(g2m_edge)^T
   bool use_pair = true;   // debug_set("gc_pair", 0): hidden GEMMs on k_gemm2 (A/B timing, bisection)
+  bool use_split = true;  // debug_set("gc_split", 0): LayerNorm GEMMs on k_gemm2 with one 512-column accumulator
   // clock
   double* clock_dev = nullptr;
   GcClock* clk_dev = nullptr;
@@ -110,6 +113,10 @@ struct GraphCastEngine : Engine {
     }
     if ((rc = walloc(m.w2, fan_out, GC_L, w2_bn))) return rc;
     if ((rc = wfill(m.w2, N("w2"), fan_out, GC_L, 0, GC_L, 0, 0, st))) return rc;
+    if (ln && fan_out == GC_L) {
+      if ((rc = walloc(m.w2s, GC_L, GC_L, 256))) return rc;
+      if ((rc = wfill(m.w2s, N("w2"), GC_L, GC_L, 0, GC_L, 0, 0, st))) return rc;
+    }
     if (!(m.b1 = keep(N("b1"), GC_L, st))) return SKY_ERR_ARG;
     {   // b2 / gamma / beta padded to the n-tile width (the kernel stages BLOCK_N entries)
       const float* b2 = param(N("b2"), (uint64_t)fan_out);
@@ -197,7 +204,8 @@ struct GraphCastEngine : Engine {
     EpiGcLn epi{xin, xout, img, yimg, m.b2, m.g, m.be, cfg.ln_eps};
     prof_begin(tag, st);
     count_launch();
-    const int rc = launch_gemm2<EpiGcLn, GC_L, 8>(A1(hid, GC_NKB), epi, m.w2.img, M, GC_L, GC_L, num_sms, st);
+    const int rc = use_split ? launch_gemm_split<EpiGcLn, 8>(A1(hid, GC_NKB), epi, m.w2s.img, M, GC_L, num_sms, st)
+                             : launch_gemm2<EpiGcLn, GC_L, 8>(A1(hid, GC_NKB), epi, m.w2.img, M, GC_L, GC_L, num_sms, st);
     prof_end(tag, st);
     return rc;
   }
@@ -240,7 +248,7 @@ struct GraphCastEngine : Engine {
     if ((rc = hidden<0>(KT_GC_MISC, A1(fimg, 1), 64, m.w1, m.b1, rows, hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
     if ((rc = ln_gemm(KT_GC_MISC, hid, m, rows, nullptr, out_f32, out_img, nullptr, st))) return rc;
     SKY_CUDA_OK(cudaStreamSynchronize(st));
-    dfree(fimg); dfree(hid); dfree(m.w1.img); dfree(m.w2.img); dfree(const_cast<float*>(m.b2));
+    dfree(fimg); dfree(hid); dfree(m.w1.img); dfree(m.w2.img); dfree(m.w2s.img); dfree(const_cast<float*>(m.b2));
     return 0;
   }
 
@@ -462,6 +470,7 @@ struct GraphCastEngine : Engine {
 
   int debug_set(const char* key, long long value) override {
     if (!strcmp(key, "gc_pair")) { use_pair = value != 0; drop_graphs(); return 0; }
+    if (!strcmp(key, "gc_split")) { use_split = value != 0; drop_graphs(); return 0; }
     return Engine::debug_set(key, value);
   }
 

@@ -27,8 +27,11 @@ __device__ __forceinline__ void add_h8(float* v, const uint4& p) {
 }
 
 // hidden = swish(acc + bias + Ta[ia[row]] + Tb[ib[row]])  ->  fp16 tile image (GC_NKB k-blocks per row tile).
-// kG = number of gathered tables (0, 1, 2).  The gathers run in the row-owner domain (lane = accumulator row): a lane
-// reads 64 contiguous bytes of its sender's / receiver's table row per 32-column chunk, issued before the TMEM read.
+// kG = number of gathered tables (0, 1, 2).  Everything after the TMEM read happens in the RE-TILED domain (lane ->
+// row = it * 8 + lane / 4, 8 columns = lane % 4): there four lanes read 64 contiguous bytes of one table row, so a gather
+// instruction touches 8 cache lines.  (First version: gathers in the row-owner domain, 32 lines per instruction — ncu showed
+// the L1TEX tag stage 67 % busy and a third of all stall samples on the first use of a gathered register.)  The table rows
+// of the next 32-column chunk are requested before the current chunk is processed.
 template <int kG>
 struct EpiGcSiluImg {
   static constexpr bool kNeedsBias = false;
@@ -40,40 +43,41 @@ struct EpiGcSiluImg {
   __device__ void run(Acc& acc, const EpiCtx& x) const {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
     const uint32_t r0 = (uint32_t)(x.row0 & 127);
-    const long long row = x.row0 + x.lane;
-    const bool valid = row < x.M;
-    const __half* pa = nullptr; const __half* pb = nullptr;
-    if (kG >= 1) pa = ta + (size_t)(valid ? __ldg(ia + row) : 0) * lda + x.n0;
-    if (kG >= 2) pb = tb + (size_t)(valid ? __ldg(ib + row) : 0) * ldb + x.n0;
+    // table rows of the four rows this lane finishes (it * 8 + rsub): indices come from the row-owner lanes by shuffle
+    const __half* pa[kG >= 1 ? 4 : 1]; const __half* pb[kG >= 2 ? 4 : 1];
+    {
+      const long long row = x.row0 + x.lane;
+      const bool valid = row < x.M;
+      const int ja = (kG >= 1 && valid) ? __ldg(ia + row) : 0;
+      const int jb = (kG >= 2 && valid) ? __ldg(ib + row) : 0;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (kG >= 1) pa[it] = ta + (size_t)__shfl_sync(0xffffffffu, ja, it * 8 + rsub) * lda + x.n0 + ch * 8;
+        if (kG >= 2) pb[it] = tb + (size_t)__shfl_sync(0xffffffffu, jb, it * 8 + rsub) * ldb + x.n0 + ch * 8;
+      }
+    }
+    uint4 ga[kG >= 1 ? 4 : 1], gb[kG >= 2 ? 4 : 1];
+    {
+      const int c = x.part * 32;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (kG >= 1) ga[it] = __ldg(reinterpret_cast<const uint4*>(pa[it] + c));
+        if (kG >= 2) gb[it] = __ldg(reinterpret_cast<const uint4*>(pb[it] + c));
+      }
+    }
     for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
-      uint4 ga[kG >= 1 ? 4 : 1], gb[kG >= 2 ? 4 : 1];
-      if (kG >= 1) {
+      uint4 na[kG >= 1 ? 4 : 1], nb[kG >= 2 ? 4 : 1];
+      const int cn = c + 32 * x.nparts < BN ? c + 32 * x.nparts : c;   // last chunk: harmless reload
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ga[j] = __ldg(reinterpret_cast<const uint4*>(pa + c) + j);
+      for (int it = 0; it < 4; ++it) {
+        if (kG >= 1) na[it] = __ldg(reinterpret_cast<const uint4*>(pa[it] + cn));
+        if (kG >= 2) nb[it] = __ldg(reinterpret_cast<const uint4*>(pb[it] + cn));
       }
-      if (kG >= 2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gb[j] = __ldg(reinterpret_cast<const uint4*>(pb + c) + j);
-      }
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8 + 4));
       {
         float v[32];
         acc.load32(c, v);
-        const float4* bp = reinterpret_cast<const float4*>(bias + x.n0 + c);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(bp + j);
-          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-        }
-        if (kG >= 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) add_h8(v + 8 * j, ga[j]);
-        }
-        if (kG >= 2) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) add_h8(v + 8 * j, gb[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
         patch_put_v(x.patch_s, x.lane, v);
       }
       __syncwarp();
@@ -84,13 +88,23 @@ struct EpiGcSiluImg {
         const int rr = it * 8 + rsub;
         const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
         const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+        float v[8] = {t0.x + b0.x, t0.y + b0.y, t0.z + b0.z, t0.w + b0.w, t1.x + b1.x, t1.y + b1.y, t1.z + b1.z, t1.w + b1.w};
+        if (kG >= 1) add_h8(v, ga[it]);
+        if (kG >= 2) add_h8(v, gb[it]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
         uint4 pk;
-        pk.x = pack_half2(t0.x, t0.y); pk.y = pack_half2(t0.z, t0.w);
-        pk.z = pack_half2(t1.x, t1.y); pk.w = pack_half2(t1.z, t1.w);
+        pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
+        pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
         if (x.row0 + rr < x.M)
           *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
       }
       __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (kG >= 1) ga[it] = na[it];
+        if (kG >= 2) gb[it] = nb[it];
+      }
     }
   }
 };
@@ -110,16 +124,24 @@ struct EpiGcLn {
     if (!xin) return;
     const long long row = e.row0 + e.lane;
     if (row >= e.M) return;
-    const char* p = reinterpret_cast<const char*>(xin + row * GC_L);
+    const char* p = reinterpret_cast<const char*>(xin + row * GC_L + e.n0);
 #pragma unroll
     for (int i = e.part; i < BN * 4 / 128; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
   }
   template <int BN, class Acc>
   __device__ void run(Acc& acc, const EpiCtx& e) const {
-    static_assert(BN == GC_L, "the LayerNorm tile spans the latent width");
+    static_assert(BN == GC_L || 2 * BN == GC_L, "the tile is the full latent width, or one half of a column-split CTA pair");
     constexpr int NG = BN / 32;
     const int rsub4 = e.lane >> 3, c4 = e.lane & 7;
     const long long rows_left = e.M - e.row0;
+    const size_t rowoff = (size_t)e.row0 * GC_L + e.n0 + c4 * 4;
+    // residual rows of the first column group: requested before the statistics pass (they come from L2: prefetch())
+    float4 xr[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + rsub4;
+      xr[it] = (xin && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + e.part * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s = 0.f, ss = 0.f;
     for (int g = e.part; g < NG; g += e.nparts) {
       float v[32];
@@ -145,10 +167,26 @@ struct EpiGcLn {
       }
       asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(32 * e.nparts) : "memory");
     }
+    if (e.x_own_bar) {
+      // column-split pair: the other half of these rows lives in the peer CTA.  Part 0 posts this CTA's sums into the
+      // peer's slot with st.async (the store itself completes the peer's mbarrier transaction: no fence, no release
+      // arrive), then every warp of the lane quarter waits for the peer's sums in its own slot.
+      if (e.part == 0) {
+        if (e.lane == 0) mbar_arrive_expect_tx(e.x_own_bar, 32 * 8);
+        __syncwarp();
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(e.x_peer_stat + e.lane * 8),
+                     "f"(s), "f"(ss), "r"(e.x_peer_bar)
+                     : "memory");
+      }
+      mbar_wait_cluster(e.x_own_bar, e.x_parity);
+      float ps, pss;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(e.x_own_stat + e.lane * 8));
+      s += ps; ss += pss;
+    }
     float rs[8], ns[8];
     {
-      const float mean = s / BN;
-      const float rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+      const float mean = s / GC_L;
+      const float rstd = rsqrtf(fmaxf(ss / GC_L - mean * mean, 0.f) + eps);
       const float nmr = -mean * rstd;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -158,14 +196,17 @@ struct EpiGcLn {
     }
     const uint32_t r0 = (uint32_t)(e.row0 & 127);
     const int odd = e.lane & 1;
-    const size_t rowoff = (size_t)e.row0 * GC_L + c4 * 4;
     for (int g = e.part; g < NG; g += e.nparts) {
       const int c = g * 32;
-      float4 xr[8];
+      float4 xn[8];   // next group's residual rows in flight while this group is normalised and stored
+      {
+        const bool more = g + e.nparts < NG;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rsub4;
-        xr[it] = (xin && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub4;
+          xn[it] = (more && xin && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + c + 32 * e.nparts)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       {
         float v[32];
@@ -176,7 +217,7 @@ struct EpiGcLn {
       const float4 bs = lds_f32x4_ro(e.svec_s + (c + c4 * 4) * 4);
       const float4 ga = lds_f32x4_ro(e.svec_s + (e.vstride + c + c4 * 4) * 4);
       const float4 be = lds_f32x4_ro(e.svec_s + (2 * e.vstride + c + c4 * 4) * 4);
-      const size_t tile_off = ((size_t)(e.row0 >> 7) * GC_NKB + (c >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
+      const size_t tile_off = ((size_t)(e.row0 >> 7) * GC_NKB + ((e.n0 + c) >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
       const uint32_t cb = (((uint32_t)c & 63u) >> 3) + (uint32_t)(c4 >> 1);
 #pragma unroll
       for (int it2 = 0; it2 < 8; it2 += 2) {
@@ -215,6 +256,8 @@ struct EpiGcLn {
         }
       }
       __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) xr[it] = xn[it];
     }
   }
 };

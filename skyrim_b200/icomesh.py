@@ -4,8 +4,8 @@ What the reference reaches through ``graphcast.load_time_loop_operational`` (/ro
 graphcast.py:51-54) builds these tables inside deepmind's un-vendored JAX package; the published construction
  is restated here with numpy / scipy:
 
-* nodes: an icosahedron refined ``levels`` times (every face split in four, new vertices pushed to the unit sphere);
-  the vertices of the coarser meshes keep their indices, so level 6 has 40,962 nodes;
+* nodes: an icosahedron refined ``levels`` times (every face split in four, new vertices pushed to the unit sphere):
+  level 6 has 40,962 nodes; ``build_graph`` renumbers them north-to-south / west-to-east (gather locality on the GPU);
 * mesh edges: the union over ALL refinement levels of the face edges, both directions (level 6: 327,660);
 * grid2mesh: every grid point within 0.6 x (longest edge of the finest mesh) of a mesh node sends to it;
 * mesh2grid: the three vertices of the finest-mesh triangle containing a grid point send to it;
@@ -176,6 +176,16 @@ def build_graph(nlat: int, nlon: int, levels: int, radius_frac: float = 0.6) -> 
     assert ng < (1 << 24)
     v, faces, ms, mr = multimesh(levels)
     nm = len(v)
+    # Renumber the mesh nodes in the GRID's order (latitude bands north to south, longitude west to east inside a band).
+    # multimesh() numbers them by refinement level, i.e. spatial neighbours are ~random rows of the node tables; the
+    # engine gathers table rows by edge index, and with this numbering the rows touched by consecutive edges (sorted by
+    # receiver) and by consecutive grid points fall into a moving window of a few bands that stays in L1 / L2.
+    lat_v, lon_v = xyz_to_latlon(v)
+    band_h = np.pi / max(2.0, np.sqrt(nm / 2.0))            # ~ one row of nodes per band
+    order = np.lexsort((lon_v, np.floor((np.pi / 2 - lat_v) / band_h)))
+    new_id = np.empty(nm, dtype=np.int64)
+    new_id[order] = np.arange(nm)
+    v, faces, ms, mr = v[order], new_id[faces], new_id[ms], new_id[mr]
     g = OrderedDict()
     g["n_grid"], g["n_mesh"] = ng, nm
     # ---- mesh edges, sorted by receiver

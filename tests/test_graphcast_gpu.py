@@ -168,3 +168,21 @@ def test_pair_hidden_gemm_matches_single_cta_kernel():
     b = eng.step(xs)
     assert torch.equal(a, b)
     eng.close()
+
+
+def test_column_split_layernorm_gemm_matches_single_accumulator_kernel():
+    """LayerNorm GEMMs run on column-split CTA pairs (k_gemm_split: 2 x 256 columns, statistics exchanged through
+    distributed shared memory); the one-accumulator k_gemm2<.., 512> path differs only in the summation order of the
+    row statistics"""
+    cfg, graph, w, x, eng = _setup(181, 360, 4, 3)   # more row tiles than CTA pairs: both tile parities, phase wrap
+    xs = torch.from_numpy(x)[None].cuda()
+    eng.set_clock(T0)
+    a = eng.step(xs).clone()
+    eng.debug_set("gc_split", 0)
+    eng.set_clock(T0)
+    b = eng.step(xs)
+    ta, tb = _tendency(cfg, a[0].cpu().numpy(), x, w), _tendency(cfg, b[0].cpu().numpy(), x, w)
+    err = np.abs(ta - tb).max() / np.abs(tb).max()
+    print(f"split vs single accumulator: max tendency difference {err:.2e} of the tendency range")
+    assert err < 2e-3
+    eng.close()
