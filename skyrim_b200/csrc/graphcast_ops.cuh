@@ -17,6 +17,26 @@ __device__ __forceinline__ float silu_f(float x) {
   // x * sigmoid(x); exp through ex2: one MUFU.EX2 + one MUFU.RCP per element
   return x * mufu_rcp(1.f + mufu_ex2(-1.4426950408889634f * x));
 }
+// table rows are re-read by many edges while operand / hidden images stream through L2 once: keep the tables
+// (L2 cache-hint policies; the plain .L2::evict_* qualifiers exist for 256-bit accesses only)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_hint(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(void* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void add_h8(float* v, const uint4& p) {
   const __half2* h = reinterpret_cast<const __half2*>(&p);
 #pragma unroll
@@ -43,6 +63,7 @@ struct EpiGcSiluImg {
   __device__ void run(Acc& acc, const EpiCtx& x) const {
     const int rsub = x.lane >> 2, ch = x.lane & 3;
     const uint32_t r0 = (uint32_t)(x.row0 & 127);
+    const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
     // table rows of the four rows this lane finishes (it * 8 + rsub): indices come from the row-owner lanes by shuffle
     const __half* pa[kG >= 1 ? 4 : 1]; const __half* pb[kG >= 2 ? 4 : 1];
     {
@@ -61,8 +82,8 @@ struct EpiGcSiluImg {
       const int c = x.part * 32;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        if (kG >= 1) ga[it] = __ldg(reinterpret_cast<const uint4*>(pa[it] + c));
-        if (kG >= 2) gb[it] = __ldg(reinterpret_cast<const uint4*>(pb[it] + c));
+        if (kG >= 1) ga[it] = ldg_hint(pa[it] + c, pol_keep);
+        if (kG >= 2) gb[it] = ldg_hint(pb[it] + c, pol_keep);
       }
     }
     for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
@@ -70,8 +91,8 @@ struct EpiGcSiluImg {
       const int cn = c + 32 * x.nparts < BN ? c + 32 * x.nparts : c;   // last chunk: harmless reload
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        if (kG >= 1) na[it] = __ldg(reinterpret_cast<const uint4*>(pa[it] + cn));
-        if (kG >= 2) nb[it] = __ldg(reinterpret_cast<const uint4*>(pb[it] + cn));
+        if (kG >= 1) na[it] = ldg_hint(pa[it] + cn, pol_keep);
+        if (kG >= 2) nb[it] = ldg_hint(pb[it] + cn, pol_keep);
       }
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8 + 4));
@@ -97,7 +118,7 @@ struct EpiGcSiluImg {
         pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
         pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
         if (x.row0 + rr < x.M)
-          *reinterpret_cast<uint4*>(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4)) = pk;
+          stg_hint(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4), pk, pol_stream);
       }
       __syncwarp();
 #pragma unroll

@@ -106,7 +106,11 @@ def test_graphcast_full_size_oracle_parity():
     x = torch.from_numpy(synthetic_graphcast_state(cfg, 0)).reshape(1, 2, cfg.n_state, cfg.nlat, cfg.nlon).cuda()
     GraphcastTimeLoop(eng).fill_forcing(x, t0)
     x = x.reshape(1, 2 * cfg.n_state, cfg.nlat, cfg.nlon).contiguous()
-    assert np.allclose(x[0, :, ::64, ::64].cpu().numpy(), fx["x0_sample"], rtol=2e-5, atol=0), "seeded IC (incl. toa forcing) differs from the fixture's"
+    xs, ref = x[0, :, ::64, ::64].cpu().numpy(), fx["x0_sample"]
+    forcing = [cfg.n_state - 1, 2 * cfg.n_state - 1]        # toa radiation: fp32 CUDA formula here, fp64 numpy in the fixture
+    prog = [c for c in range(2 * cfg.n_state) if c not in forcing]
+    assert np.array_equal(xs[prog], ref[prog]), "seeded IC differs from the fixture's"
+    assert np.abs(xs[forcing] - ref[forcing]).max() <= 2e-5 * ref[forcing].max(), "toa forcing differs from the fixture's"
     eng.set_clock(t0)
     y = eng.step(x)
     s = compare_graphcast(y[0], x[0], w["norm.diff_std"], fx, cfg)
