@@ -23,7 +23,7 @@ from urllib.parse import urlparse
 
 from loguru import logger
 
-AVAILABLE_MODELS = ["pangu", "fourcastnet_v2"]
+AVAILABLE_MODELS = ["pangu", "fourcastnet_v2", "graphcast"]
 LOCAL_CACHE = os.path.join(os.path.expanduser("~"), ".cache", "skyrim")
 OUTPUT_DIR = str(Path.cwd() / "outputs")
 

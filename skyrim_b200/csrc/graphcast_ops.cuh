@@ -49,9 +49,12 @@ __device__ __forceinline__ void add_h8(float* v, const uint4& p) {
 // hidden = swish(acc + bias + Ta[ia[row]] + Tb[ib[row]])  ->  fp16 tile image (GC_NKB k-blocks per row tile).
 // kG = number of gathered tables (0, 1, 2).  Everything after the TMEM read happens in the RE-TILED domain (lane ->
 // row = it * 8 + lane / 4, 8 columns = lane % 4): there four lanes read 64 contiguous bytes of one table row, so a gather
-// instruction touches 8 cache lines.  (First version: gathers in the row-owner domain, 32 lines per instruction — ncu showed
-// the L1TEX tag stage 67 % busy and a third of all stall samples on the first use of a gathered register.)  The table rows
-// of the next 32-column chunk are requested before the current chunk is processed.
+// instruction touches 8 cache lines instead of 32 (row-owner gathers kept the L1TEX tag stage 67 % busy).
+// Latency structure (profiles/r2e_graphcast.md): a gather is an L2 round trip of 1 - 2 us, and tcgen05.wait::ld also waits
+// for the thread's outstanding global loads, so a register prefetch of the NEXT chunk is waited for at the current chunk's
+// TMEM read and hides nothing (measured: no change).  What does help is fewer exposures: the table rows of TWO 32-column
+// chunks are requested together, in front of the first chunk's TMEM read; the second chunk then finds its rows in
+// registers.  A warp handles 4 chunks per 256-column tile: 2 exposed round trips instead of 4.
 template <int kG>
 struct EpiGcSiluImg {
   static constexpr bool kNeedsBias = false;
@@ -77,54 +80,50 @@ struct EpiGcSiluImg {
         if (kG >= 2) pb[it] = tb + (size_t)__shfl_sync(0xffffffffu, jb, it * 8 + rsub) * ldb + x.n0 + ch * 8;
       }
     }
-    uint4 ga[kG >= 1 ? 4 : 1], gb[kG >= 2 ? 4 : 1];
-    {
-      const int c = x.part * 32;
+    const int cstep = 32 * x.nparts;
+    for (int c0 = x.part * 32; c0 < BN; c0 += 2 * cstep) {
+      uint4 ga[kG >= 1 ? 8 : 1], gb[kG >= 2 ? 8 : 1];     // [chunk u][it]
+      const bool two = c0 + cstep < BN;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (kG >= 1) ga[it] = ldg_hint(pa[it] + c, pol_keep);
-        if (kG >= 2) gb[it] = ldg_hint(pb[it] + c, pol_keep);
+      for (int u = 0; u < 2; ++u) {
+        const int cu = (u && !two) ? c0 : c0 + u * cstep;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          if (kG >= 1) ga[u * 4 + it] = ldg_hint(pa[it] + cu, pol_keep);
+          if (kG >= 2) gb[u * 4 + it] = ldg_hint(pb[it] + cu, pol_keep);
+        }
       }
-    }
-    for (int c = x.part * 32; c < BN; c += 32 * x.nparts) {
-      uint4 na[kG >= 1 ? 4 : 1], nb[kG >= 2 ? 4 : 1];
-      const int cn = c + 32 * x.nparts < BN ? c + 32 * x.nparts : c;   // last chunk: harmless reload
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (kG >= 1) na[it] = ldg_hint(pa[it] + cn, pol_keep);
-        if (kG >= 2) nb[it] = ldg_hint(pb[it] + cn, pol_keep);
-      }
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8 + 4));
-      {
-        float v[32];
-        acc.load32(c, v);
-        patch_put_v(x.patch_s, x.lane, v);
-      }
-      __syncwarp();
-      const int col = x.n0 + c;
-      uint8_t* ibase = out + ((size_t)(x.row0 >> 7) * GC_NKB + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * cstep;
+        if (u && !two) break;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + x.n0 + c + ch * 8 + 4));
+        {
+          float v[32];
+          acc.load32(c, v);
+          patch_put_v(x.patch_s, x.lane, v);
+        }
+        __syncwarp();
+        const int col = x.n0 + c;
+        uint8_t* ibase = out + ((size_t)(x.row0 >> 7) * GC_NKB + (col >> 6)) * (size_t)G2_A_BYTES + r0 * 128;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int rr = it * 8 + rsub;
-        const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
-        const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
-        float v[8] = {t0.x + b0.x, t0.y + b0.y, t0.z + b0.z, t0.w + b0.w, t1.x + b1.x, t1.y + b1.y, t1.z + b1.z, t1.w + b1.w};
-        if (kG >= 1) add_h8(v, ga[it]);
-        if (kG >= 2) add_h8(v, gb[it]);
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rsub;
+          const float4 t0 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch));
+          const float4 t1 = lds_f32x4(patchv_addr(x.patch_s, rr, 2 * ch + 1));
+          float v[8] = {t0.x + b0.x, t0.y + b0.y, t0.z + b0.z, t0.w + b0.w, t1.x + b1.x, t1.y + b1.y, t1.z + b1.z, t1.w + b1.w};
+          if (kG >= 1) add_h8(v, ga[u * 4 + it]);
+          if (kG >= 2) add_h8(v, gb[u * 4 + it]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-        uint4 pk;
-        pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
-        pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
-        if (x.row0 + rr < x.M)
-          stg_hint(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4), pk, pol_stream);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (kG >= 1) ga[it] = na[it];
-        if (kG >= 2) gb[it] = nb[it];
+          for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+          uint4 pk;
+          pk.x = pack_half2(v[0], v[1]); pk.y = pack_half2(v[2], v[3]);
+          pk.z = pack_half2(v[4], v[5]); pk.w = pack_half2(v[6], v[7]);
+          if (x.row0 + rr < x.M)
+            stg_hint(ibase + rr * 128 + (((((col & 63) >> 3) + ch) ^ (rr & 7)) << 4), pk, pol_stream);
+        }
+        __syncwarp();
       }
     }
   }

@@ -56,9 +56,10 @@ def main(model_name, date, time, lead_time, list_models, initial_conditions, out
         raise click.UsageError("--modal: remote execution through Modal is outside this build (SURVEY.md section 2); run locally")
     kw = {"weight_seed": weight_seed, "device": device}
     if grid:
-        from .config import pangu_small, sfno_small
+        from .config import graphcast_small, pangu_small, sfno_small
         nlat, nlon = (int(v) for v in grid.lower().split("x"))
-        kw["cfg"] = pangu_small(nlat, nlon) if model_name == "pangu" else sfno_small(nlat, nlon)
+        kw["cfg"] = (pangu_small(nlat, nlon) if model_name == "pangu" else graphcast_small(nlat, nlon) if model_name == "graphcast"
+                     else sfno_small(nlat, nlon))
     paths = run_forecast(model_name, date, time, lead_time, list_models, initial_conditions, output_dir, filter_vars, **kw)
     for p in paths:
         print(p)

@@ -122,7 +122,7 @@ def test_rollout_predict_and_accessors(tmp_path):
 
 def test_skyrim_facade_validates_names():
     from skyrim_b200.core.skyrim import Skyrim
-    assert Skyrim.list_available_models() == ["pangu", "fourcastnet_v2"]
+    assert Skyrim.list_available_models() == ["pangu", "fourcastnet_v2", "graphcast"]
     with pytest.raises(ValueError):
         Skyrim("not_a_model")
 
