@@ -322,6 +322,8 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
         x0 = base[None].repeat(M, 1, 1, 1).to(dev).contiguous()
     reset_clock = (lambda: eng.set_clock(GC_T0)) if gc else (lambda: None)   # every chain below restarts from the IC's time
     sigma = torch.from_numpy(channel_stats(CH)[1]).to(dev)
+    if gc:   # both time slices are perturbed, the toa forcing channel of each is not
+        sigma = torch.cat([sigma, sigma]); sigma[cfg.n_state - 1] = 0.0; sigma[2 * cfg.n_state - 1] = 0.0
     first = 1 if d.rank == 0 else 0
     if M - first > 0:
         perturb_ic(x0[first:], sigma, 0.05, seed=0, member0=d.rank * M + first)
