@@ -197,7 +197,8 @@ struct GraphCastEngine : Engine {
     else
       rc = launch_gemm2<EpiGcSiluImg<kG>, 256, 8>(A, epi, w.img, M, GC_L, Kp, num_sms, st);
     prof_end(tag, st);
-    return rc;
+    // fp16-range guard (engine.h; a no-op unless enabled): class 5 hidden images, 0 latent / update images, 6 per-node tables
+    return rc ? rc : range_scan(5, out, (size_t)(M / 128) * GC_NKB * G2_A_BYTES, st);
   }
   int ln_gemm(int tag, const uint8_t* hid, const Mlp& m, long long M, const float* xin, float* xout, uint8_t* img, uint8_t* yimg,
               cudaStream_t st) {
@@ -207,7 +208,9 @@ struct GraphCastEngine : Engine {
     const int rc = use_split ? launch_gemm_split<EpiGcLn, 8>(A1(hid, GC_NKB), epi, m.w2s.img, M, GC_L, num_sms, st)
                              : launch_gemm2<EpiGcLn, GC_L, 8>(A1(hid, GC_NKB), epi, m.w2.img, M, GC_L, GC_L, num_sms, st);
     prof_end(tag, st);
-    return rc;
+    if (rc) return rc;
+    if (img) if (int r2 = range_scan(0, img, (size_t)(M / 128) * GC_NKB * G2_A_BYTES, st)) return r2;
+    return yimg ? range_scan(0, yimg, (size_t)(M / 128) * GC_NKB * G2_A_BYTES, st) : 0;
   }
   // per-node table: T (M, N) fp16 row-major = A W^T
   int table(int tag, const uint8_t* aimg, const WImg& w, long long M, __half* out, cudaStream_t st) {
@@ -217,7 +220,7 @@ struct GraphCastEngine : Engine {
     count_launch();
     const int rc = launch_gemm2<Epi2F16<false, false>, 256, 8>(A1(aimg, GC_NKB), epi, w.img, M, w.N, GC_L, num_sms, st);
     prof_end(tag, st);
-    return rc;
+    return rc ? rc : range_scan(6, out, (size_t)M * w.N * 2, st);
   }
   int segsum(int tag, const uint8_t* yimg, const SegPlan& sp, uint8_t* out, cudaStream_t st) {
     prof_begin(tag, st);
@@ -451,6 +454,7 @@ struct GraphCastEngine : Engine {
         if ((rc = hidden<0>(KT_GC_HIDDEN, a, 4 * L, m2g_grid.w1, m2g_grid.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
       }
       if ((rc = ln_gemm(KT_GC_LN, w.hid, m2g_grid, Ng, w.vg, w.vg, w.vg_img, nullptr, st))) return rc;
+      if ((rc = range_scan(0, w.feat, img_bytes(Ng, GC_FEAT_KP / 64), st))) return rc;
       if (stop_after == 100) continue;
       if ((rc = hidden<0>(KT_GC_HIDDEN, A1(w.vg_img, GC_NKB), L, out_mlp.w1, out_mlp.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
       {
@@ -477,7 +481,8 @@ struct GraphCastEngine : Engine {
   int debug_copy(const char* what, float* dst, uint64_t max_floats, void* ws_base, int, cudaStream_t st) override {
     const Ws w = carve(ws_base);
     const float* src = nullptr; uint64_t n = 0;
-    if (!strcmp(what, "vg")) { src = w.vg; n = (uint64_t)Ng * GC_L; }
+    if (!strcmp(what, "range")) { src = range_dev; n = 8; if (!src) { set_error("range guard was never enabled"); return SKY_ERR_STATE; } }
+    else if (!strcmp(what, "vg")) { src = w.vg; n = (uint64_t)Ng * GC_L; }
     else if (!strcmp(what, "vm")) { src = w.vm; n = (uint64_t)Nm * GC_L; }
     else if (!strcmp(what, "em")) { src = w.em; n = (uint64_t)Em * GC_L; }
     else if (!strcmp(what, "vm0")) { src = vm0_f32; n = (uint64_t)Nm * GC_L; }

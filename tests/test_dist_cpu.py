@@ -50,3 +50,38 @@ def test_member_ranges_cover_ensemble_exactly_once():
     for world, m in [(1, 1), (2, 4), (8, 4)]:
         ids = [i for r in range(world) for i in member_range(r, m)]
         assert ids == list(range(world * m))
+
+
+def _worker_graphcast(rank, world, port, q):
+    """GraphCast: the arena also carries the graph tables (built on every rank: their shapes size the manifest)"""
+    from skyrim_b200.config import graphcast_small
+    from skyrim_b200.icomesh import build_graph, graph_arena_entries
+    from skyrim_b200.weights import graphcast_param_shapes, make_graphcast_weights
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = graphcast_small(21, 48, 1, 512, 1)
+    gent = graph_arena_entries(build_graph(cfg.nlat, cfg.nlon, cfg.mesh_levels, cfg.radius_frac))
+    shapes = graphcast_param_shapes(cfg)
+    shapes.update({k: v.shape for k, v in gent.items()})
+    w = None
+    if rank == 0:
+        w = make_graphcast_weights(cfg, 3); w.update(gent)
+    arena, manifest = broadcast_arena(w, shapes, torch.device("cpu"), rank, world)
+    ref = make_graphcast_weights(cfg, 3); ref.update(gent)
+    ok = len(manifest) == len(ref)
+    for d, (k, a) in zip(manifest, ref.items()):
+        ok &= d.name.decode() == k and np.array_equal(arena[d.offset:d.offset + d.count].numpy(), np.asarray(a, np.float32).reshape(-1))
+    q.put((rank, bool(ok), float(arena.double().sum())))
+    dist.destroy_process_group()
+
+
+def test_graphcast_arena_with_graph_tables_broadcasts():
+    world, port = 2, 29519
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_graphcast, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    [p.join(30) for p in ps]
+    assert all(r[1] for r in res), res
+    assert res[0][2] == res[1][2]

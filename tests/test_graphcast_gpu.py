@@ -186,3 +186,49 @@ def test_column_split_layernorm_gemm_matches_single_accumulator_kernel():
     print(f"split vs single accumulator: max tendency difference {err:.2e} of the tendency range")
     assert err < 2e-3
     eng.close()
+
+
+def test_rollout_saves_every_step_and_cli(tmp_path):
+    """GraphcastModel.rollout(save=True) (graphcast.py:144-177): one file per step with two time slices, the forecast CLI
+    drives the same path"""
+    from skyrim_b200 import xr_shim as xr
+    from skyrim_b200.core import Skyrim
+    cfg = graphcast_small(41, 96, 2, 512, 2)
+    model = Skyrim("graphcast", ic_source="synthetic", cfg=cfg)
+    pred, paths = model.predict("20240404", "0600", 18, save=True, save_config=dict(output_dir=str(tmp_path), file_type="netcdf"))
+    assert len(paths) == 3
+    last = xr.open_dataarray(paths[-1])
+    assert last.shape == (2, 83, 41, 96)
+    assert np.array_equal(np.asarray(last.values, dtype=np.float32), pred.prediction.values.astype(np.float32))
+    first = xr.open_dataarray(paths[0])
+    second = xr.open_dataarray(paths[1])
+    assert np.array_equal(first.values[1], second.values[0]), "successive files overlap by one time slice, as in the reference"
+    from click.testing import CliRunner
+    from skyrim_b200.forecast import main
+    r = CliRunner().invoke(main, ["-m", "graphcast", "-d", "20240404", "-t", "0000", "-l", "12", "-o", str(tmp_path / "cli"),
+                                  "--grid", "41x96"])
+    assert r.exit_code == 0, r.output
+
+
+def test_fp16_range_guard_graphcast():
+    """guarded step: max |value| of the fp16 operand image classes stays far inside the fp16 range on synthetic weights; an
+    inflated first-layer weight is refused"""
+    from skyrim_b200 import _ffi
+    cfg, graph, w, x, eng = _setup(41, 96, 2, 2)
+    xs = torch.from_numpy(x)[None].cuda()
+    eng.set_clock(T0)
+    y_plain = eng.step(xs).clone()
+    eng.set_clock(T0)
+    y, ranges = eng.step_guarded(xs)
+    assert torch.equal(y, y_plain)
+    assert set(ranges) >= {"token_images", "hidden_images", "spectral_images"}, ranges
+    assert all(0 < v < 2000 for v in ranges.values()), ranges
+    eng.close()
+    from skyrim_b200.engine import StepEngine
+    w2 = dict(w); w2["proc0.edge.w1"] = w["proc0.edge.w1"] * 1.0e5
+    eng2 = StepEngine(cfg, 0, graph=graph)
+    eng2.load_weights(w2)
+    eng2.set_clock(T0)
+    with pytest.raises(_ffi.SkyError):
+        eng2.step_guarded(xs)
+    eng2.close()
