@@ -438,8 +438,9 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
     if e2e:
         sbytes = cfg.n_channels * cfg.nlat * cfg.nlon * 4 * M
         rec["e2e"] = {"value": d.world * M * 1000.0 / e2e_max, "unit": UNIT, "ms_per_step": e2e_max,
-                      "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes,
-                      "path": "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host",
+                      "h2d_bytes_per_step": sbytes, "d2h_bytes_per_step": sbytes // 2 if gc else sbytes,
+                      "path": ("GraphcastTimeLoop.step_host: both time slices pinned host -> HBM, sky_model_step, the NEW time slice HBM -> "
+                               "pinned host" if gc else "TimeLoop.step_host: pinned host -> HBM, sky_model_step, HBM -> pinned host"),
                       "rollout_every_state_to_host": None if roll_ms is None else {
                           "ms_per_step": roll_ms, "value": M * 1000.0 / roll_ms, "unit": UNIT, "d2h_bytes_per_step": sbytes,
                           "h2d_bytes_per_step": 0, "rank": d.rank,
