@@ -83,7 +83,7 @@ struct EpiCtx {
   int patch_stride = G2_PATCH_FLOATS * 4;   // bytes between the patches of consecutive warps
   // per-row-group scratch an epilogue may cache across the n-tiles of one m-tile (EpiQkvWin: destination row of this lane)
   mutable long long aux_row0 = -1;
-  mutable int aux = 0;
+  mutable int aux = 0, aux2 = 0;
   // row-statistics exchange with the peer CTA of a column-split pair (gemm_split.cuh); x_own_bar == nullptr elsewhere
   uint64_t* x_own_bar = nullptr;   // completes when the peer's 32 (sum, sum of squares) pairs of this lane quarter landed
   uint32_t x_own_stat = 0;         // shared-space address of this CTA's slot: 32 x {float s, ss}

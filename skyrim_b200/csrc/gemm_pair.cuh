@@ -176,6 +176,7 @@ k_gemm_pair(const uint8_t* __restrict__ Aimg,   // fp16 tile image of A (tokens,
       for (int nt = 0; nt < num_n_tiles; ++nt, ++cnt) {
         const uint32_t buf = cnt & 1, use = cnt >> 1;
         ctx.n0 = nt * Cfg::NT;
+        if constexpr (Epi::kHasPre) epi.template pre<Cfg::NT>(ctx);   // work that can start before the accumulator is ready
         mbar_wait(&acc_full[buf], use & 1);
         tc_fence_after();
         AccTmem2 acc{tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::NT};

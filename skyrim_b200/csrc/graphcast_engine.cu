@@ -59,6 +59,7 @@ struct GraphCastEngine : Engine {
   float *e_mesh_f32 = nullptr, *vm0_f32 = nullptr;
   __half* g2m_tr = nullptr;             // (Nm, 512): embedded mesh nodes x W1r(g2m_edge)^T
   bool use_pair = true;   // debug_set("gc_pair", 0): hidden GEMMs on k_gemm2 (A/B timing, bisection)
+  bool l2_prefetch = true;  // debug_set("gc_prefetch", 0)
   bool use_split = true;  // debug_set("gc_split", 0): LayerNorm GEMMs on k_gemm2 with one 512-column accumulator
   // clock
   double* clock_dev = nullptr;
@@ -186,6 +187,7 @@ struct GraphCastEngine : Engine {
     if (w.BN != 256 || w.Kp != Kp) { set_error("internal: hidden GEMM weight shape"); return SKY_ERR_STATE; }
     EpiGcSiluImg<kG> epi{};
     epi.out = out; epi.bias = b1; epi.ta = ta; epi.lda = lda; epi.ia = ia; epi.tb = tb; epi.ldb = ldb; epi.ib = ib;
+    epi.l2_prefetch = l2_prefetch && M > 4 * Nm ? 1 : 0;   // grid-sized tables only (the mesh tables are L2 resident)
     prof_begin(tag, st);
     count_launch();
     int rc;
@@ -431,7 +433,10 @@ struct GraphCastEngine : Engine {
         if ((rc = table(KT_GC_TABLE, w.vm_img, proc_wsr[i], Nm, w.tm, st))) return rc;
         if ((rc = hidden<2>(KT_GC_HIDDEN, A1(em_in_img, GC_NKB), L, proc_edge[i].w1, proc_edge[i].b1, Em, w.hid_m, w.tm, 2 * L, mesh_s, w.tm + L,
                             2 * L, mesh_r, st))) return rc;
-        if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_edge[i], Em, em_in, w.em, w.em_img, w.ym_img, st))) return rc;
+        // the edge latents are not read after the last layer: only the update image (for the aggregation) is produced there
+        const bool last = i == cfg.layers - 1 && stop_after == 99;
+        if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_edge[i], Em, last ? nullptr : em_in, last ? nullptr : w.em, last ? nullptr : w.em_img,
+                          w.ym_img, st))) return rc;
         if ((rc = segsum(KT_GC_AGG, w.ym_img, mesh_seg, w.agg_img, st))) return rc;
         if ((rc = hidden<0>(KT_GC_HIDDEN, A2(w.vm_img, w.agg_img), 2 * L, proc_node[i].w1, proc_node[i].b1, Nm, w.hid_m, nullptr, 0, nullptr, nullptr, 0,
                             nullptr, st))) return rc;
@@ -475,6 +480,7 @@ struct GraphCastEngine : Engine {
   int debug_set(const char* key, long long value) override {
     if (!strcmp(key, "gc_pair")) { use_pair = value != 0; drop_graphs(); return 0; }
     if (!strcmp(key, "gc_split")) { use_split = value != 0; drop_graphs(); return 0; }
+    if (!strcmp(key, "gc_prefetch")) { l2_prefetch = value != 0; drop_graphs(); return 0; }
     return Engine::debug_set(key, value);
   }
 

@@ -28,6 +28,8 @@ def main():
     t_load = time.time() - t0
     if "nopair" in sys.argv:
         eng.debug_set("gc_pair", 0)
+    if "noprefetch" in sys.argv:
+        eng.debug_set("gc_prefetch", 0)
     if "nosplit" in sys.argv:
         eng.debug_set("gc_split", 0)
     loop = GraphcastTimeLoop(eng)
