@@ -232,3 +232,29 @@ def test_fp16_range_guard_graphcast():
     with pytest.raises(_ffi.SkyError):
         eng2.step_guarded(xs)
     eng2.close()
+
+
+def test_timeloop_generator_and_host_step_agree_with_the_stepper():
+    """TimeLoop protocol (first yield = the initial condition's last slice), the stepper protocol of graphcast.py:110,118 and
+    the host-in / host-out step of bench.py's e2e all run the same chain"""
+    from skyrim_b200.timeloop import GraphcastTimeLoop
+    cfg, graph, w, x, eng = _setup(41, 96, 2, 1)
+    loop = GraphcastTimeLoop(eng)
+    t0 = datetime.datetime(2024, 5, 1)
+    x5 = torch.from_numpy(x).reshape(1, 2, cfg.n_state, cfg.nlat, cfg.nlon)
+    gen = loop(t0, x5)
+    t, first, _ = next(gen)
+    assert t == t0 and torch.equal(first.cpu(), x5[:, 1])
+    t1, y1, _ = next(gen)
+    t2, y2, _ = next(gen)
+    assert t2 == t0 + 2 * loop.time_step
+    state = loop.stepper.initialize(x5, t0)
+    state, o1 = loop.stepper.step(state)
+    state, o2 = loop.stepper.step(state)
+    assert torch.equal(o1, y1) and torch.equal(o2, y2) and state[0] == t2
+    xh = x5.reshape(1, -1, cfg.nlat, cfg.nlon).contiguous().pin_memory()
+    eng.set_clock(t0)
+    h = loop.step_host(xh)
+    h = loop.step_host(h)
+    assert torch.equal(h[1], y2.cpu()) and torch.equal(h[0], y1.cpu())
+    eng.close()
