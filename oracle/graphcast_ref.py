@@ -77,14 +77,16 @@ class GraphCastRef:
     def mlp(self, name: str, parts, ln: bool = True, table_parts=()):
         """Linear -> swish -> Linear (-> LayerNorm) on the concatenation of ``parts`` along the feature axis, row chunked.
         emulate="fp16" rounds every GEMM operand to half; emulate="fp16t" additionally rounds the first-layer partial
-        products of the parts listed in ``table_parts`` (the engine stores those per-node tables in fp16)."""
+        products of the parts listed in ``table_parts`` (the engine stores those per-node tables in fp16); emulate="fp16s"
+        additionally keeps the grid-node and mesh-edge residual streams in half between layers (``tendency``), as the engine
+        does (they exist only as fp16 operand images there)."""
         w1, b1, w2, b2 = (self.w[f"{name}.{k}"] for k in ("w1", "b1", "w2", "b2"))
         n = parts[0].shape[0]
         out = torch.empty(n, w2.shape[0], dtype=self.dtype)
         w1q, w2q = self._q(w1), self._q(w2)
         for r0 in range(0, n, self.CHUNK):
             sl = slice(r0, min(n, r0 + self.CHUNK))
-            if self.emulate == "fp16t" and table_parts:
+            if self.emulate in ("fp16t", "fp16s") and table_parts:
                 h, c0 = b1.clone().expand(sl.stop - sl.start, -1).clone(), 0
                 for i, p in enumerate(parts):
                     pp = self._q(p[sl]) @ w1q[:, c0:c0 + p.shape[1]].T
@@ -144,15 +146,16 @@ class GraphCastRef:
         st = self.static_embeddings()
         nm = self.g["n_mesh"]
         tap = (lambda k, v: taps.__setitem__(k, v.clone())) if taps is not None else (lambda k, v: None)
+        qs = (lambda t: t.half().to(self.dtype)) if self.emulate == "fp16s" else (lambda t: t)   # fp16-only residual streams
         # encoder
-        vg = self.mlp("enc.grid_embed", [self.features(x, t_seconds)])
+        vg = qs(self.mlp("enc.grid_embed", [self.features(x, t_seconds)]))
         tap("grid_embed", vg)
         vm = st["vm"]
         s, r = ix["g2m.senders"], ix["g2m.receivers"]
         e = self.mlp("enc.g2m_edge", [st["e_g2m"], vg[s], vm[r]], table_parts=(1, 2))
         agg = torch.zeros(nm, cfg.latent, dtype=self.dtype).index_add_(0, r, e)
         vm = vm + self.mlp("enc.g2m_mesh", [vm, agg])
-        vg = vg + self.mlp("enc.g2m_grid", [vg])
+        vg = qs(vg + self.mlp("enc.g2m_grid", [vg]))
         tap("enc_mesh", vm); tap("enc_grid", vg)
         # processor
         em = st["e_mesh"]
@@ -161,7 +164,7 @@ class GraphCastRef:
             e = self.mlp(f"proc{i}.edge", [em, vm[s], vm[r]], table_parts=(1, 2))
             agg = torch.zeros(nm, cfg.latent, dtype=self.dtype).index_add_(0, r, e)
             vm_new = vm + self.mlp(f"proc{i}.node", [vm, agg])
-            em = em + e
+            em = qs(em + e)
             vm = vm_new
             tap(f"proc{i}_mesh", vm)
         # decoder
@@ -169,7 +172,7 @@ class GraphCastRef:
         e = self.mlp("dec.m2g_edge", [st["e_m2g"], vm[s], vg[r]], table_parts=(1, 2))
         agg = torch.zeros(cfg.n_grid, cfg.latent, dtype=self.dtype).index_add_(0, r, e)
         del e
-        vg = vg + self.mlp("dec.m2g_grid", [vg, agg])
+        vg = qs(vg + self.mlp("dec.m2g_grid", [vg, agg]))
         tap("dec_grid", vg)
         out = self.mlp("dec.out", [vg], ln=False)
         return out[:, :cfg.n_prog]

@@ -56,7 +56,7 @@ struct GraphCastEngine : Engine {
   } mesh_seg, g2m_seg;
   // input-independent embeddings
   uint8_t *e_g2m_img = nullptr, *e_m2g_img = nullptr, *e_mesh_img = nullptr, *vm0_img = nullptr;
-  float *e_mesh_f32 = nullptr, *vm0_f32 = nullptr;
+  float* vm0_f32 = nullptr;
   __half* g2m_tr = nullptr;             // (Nm, 512): embedded mesh nodes x W1r(g2m_edge)^T
   bool use_pair = true;   // debug_set("gc_pair", 0): hidden GEMMs on k_gemm2 (A/B timing, bisection)
   bool l2_prefetch = true;  // debug_set("gc_prefetch", 0)
@@ -202,13 +202,23 @@ struct GraphCastEngine : Engine {
     // fp16-range guard (engine.h; a no-op unless enabled): class 5 hidden images, 0 latent / update images, 6 per-node tables
     return rc ? rc : range_scan(5, out, (size_t)(M / 128) * GC_NKB * G2_A_BYTES, st);
   }
+  template <int kRes>
+  int ln_launch(const uint8_t* hid, const Mlp& m, long long M, const float* xin, float* xout, uint8_t* img, uint8_t* yimg,
+                const uint8_t* xin_img, cudaStream_t st) {
+    EpiGcLn<kRes> epi{xin, xout, img, yimg, m.b2, m.g, m.be, cfg.ln_eps};
+    epi.xin_img = xin_img;
+    return use_split ? launch_gemm_split<EpiGcLn<kRes>, 8>(A1(hid, GC_NKB), epi, m.w2s.img, M, GC_L, num_sms, st)
+                     : launch_gemm2<EpiGcLn<kRes>, GC_L, 8>(A1(hid, GC_NKB), epi, m.w2.img, M, GC_L, GC_L, num_sms, st);
+  }
+  // xin (fp32 rows) or xin_img (fp16 image) is the residual source; at most one of them
   int ln_gemm(int tag, const uint8_t* hid, const Mlp& m, long long M, const float* xin, float* xout, uint8_t* img, uint8_t* yimg,
-              cudaStream_t st) {
-    EpiGcLn epi{xin, xout, img, yimg, m.b2, m.g, m.be, cfg.ln_eps};
+              cudaStream_t st, const uint8_t* xin_img = nullptr) {
     prof_begin(tag, st);
     count_launch();
-    const int rc = use_split ? launch_gemm_split<EpiGcLn, 8>(A1(hid, GC_NKB), epi, m.w2s.img, M, GC_L, num_sms, st)
-                             : launch_gemm2<EpiGcLn, GC_L, 8>(A1(hid, GC_NKB), epi, m.w2.img, M, GC_L, GC_L, num_sms, st);
+    int rc;
+    if (xin) rc = ln_launch<1>(hid, m, M, xin, xout, img, yimg, nullptr, st);
+    else if (xin_img) rc = ln_launch<2>(hid, m, M, nullptr, xout, img, yimg, xin_img, st);
+    else rc = ln_launch<0>(hid, m, M, nullptr, xout, img, yimg, nullptr, st);
     prof_end(tag, st);
     if (rc) return rc;
     if (img) if (int r2 = range_scan(0, img, (size_t)(M / 128) * GC_NKB * G2_A_BYTES, st)) return r2;
@@ -318,17 +328,16 @@ struct GraphCastEngine : Engine {
     e_m2g_img = dalloc<uint8_t>(img_bytes(E3, GC_NKB), true);
     e_mesh_img = dalloc<uint8_t>(img_bytes(Em, GC_NKB), true);
     vm0_img = dalloc<uint8_t>(img_bytes(Nm, GC_NKB), true);
-    e_mesh_f32 = dalloc<float>((size_t)pad128(Em) * L, true);
     vm0_f32 = dalloc<float>((size_t)pad128(Nm) * L, true);
     g2m_tr = dalloc<__half>((size_t)pad128(Nm) * L, true);
-    if (!e_g2m_img || !e_m2g_img || !e_mesh_img || !vm0_img || !e_mesh_f32 || !vm0_f32 || !g2m_tr) return SKY_ERR_NOMEM;
+    if (!e_g2m_img || !e_m2g_img || !e_mesh_img || !vm0_img || !vm0_f32 || !g2m_tr) return SKY_ERR_NOMEM;
     const float* f;
     if (!(f = param("graph.mesh.node_feat", (uint64_t)Nm * 3))) return SKY_ERR_ARG;
     if ((rc = static_embed("enc.mesh_embed", f, Nm, 3, vm0_img, vm0_f32, st))) return rc;
     if (!(f = param("graph.g2m.edge_feat", (uint64_t)Eg * 4))) return SKY_ERR_ARG;
     if ((rc = static_embed("enc.g2m_edge_embed", f, Eg, 4, e_g2m_img, nullptr, st))) return rc;
     if (!(f = param("graph.mesh.edge_feat", (uint64_t)Em * 4))) return SKY_ERR_ARG;
-    if ((rc = static_embed("proc.edge_embed", f, Em, 4, e_mesh_img, e_mesh_f32, st))) return rc;
+    if ((rc = static_embed("proc.edge_embed", f, Em, 4, e_mesh_img, nullptr, st))) return rc;
     {
       if (!(f = param("graph.m2g.edge_feat", (uint64_t)3 * Ng * 4))) return SKY_ERR_ARG;
       float* fp = dalloc<float>((size_t)E3 * 4);
@@ -353,7 +362,7 @@ struct GraphCastEngine : Engine {
   // ---- workspace --------------------------------------------------------------------------------------------------
   struct Ws {
     uint8_t *feat, *hid, *vg_img, *yimg, *vm_img, *em_img, *ym_img, *agg_img, *hid_m;
-    float *vg, *vm, *em;
+    float* vm;
     __half *tg, *tm;
     size_t total;
   };
@@ -364,14 +373,12 @@ struct GraphCastEngine : Engine {
     const long long Emax = E3 > pad128(Eg) ? E3 : pad128(Eg);
     w.feat = (uint8_t*)take(img_bytes(Ng, GC_FEAT_KP / 64));
     w.hid = (uint8_t*)take(img_bytes(Emax, GC_NKB));          // hidden activations of the grid-sized / edge-sized MLPs
-    w.vg = (float*)take((size_t)Ngp * GC_L * 4);
     w.vg_img = (uint8_t*)take(img_bytes(Ng, GC_NKB));
     w.tg = (__half*)take((size_t)Ngp * GC_L * 2);              // grid-node table (g2m sender / m2g receiver)
     w.yimg = (uint8_t*)take(img_bytes(Emax, GC_NKB));          // edge updates of the grid2mesh / mesh2grid step
     w.vm = (float*)take((size_t)pad128(Nm) * GC_L * 4);
     w.vm_img = (uint8_t*)take(img_bytes(Nm, GC_NKB));
     w.tm = (__half*)take((size_t)pad128(Nm) * 2 * GC_L * 2);   // mesh-node table [W1s | W1r]
-    w.em = (float*)take((size_t)pad128(Em) * GC_L * 4);
     w.em_img = (uint8_t*)take(img_bytes(Em, GC_NKB));
     w.ym_img = (uint8_t*)take(img_bytes(Em, GC_NKB));
     w.agg_img = (uint8_t*)take(img_bytes(Nm, GC_NKB));
@@ -414,7 +421,7 @@ struct GraphCastEngine : Engine {
       SKY_CUDA_OK(cudaGetLastError());
       if ((rc = hidden<0>(KT_GC_HIDDEN, A1(w.feat, GC_FEAT_KP / 64), GC_FEAT_KP, grid_embed.w1, grid_embed.b1, Ng, w.hid, nullptr, 0, nullptr,
                           nullptr, 0, nullptr, st))) return rc;
-      if ((rc = ln_gemm(KT_GC_LN, w.hid, grid_embed, Ng, nullptr, w.vg, w.vg_img, nullptr, st))) return rc;
+      if ((rc = ln_gemm(KT_GC_LN, w.hid, grid_embed, Ng, nullptr, nullptr, w.vg_img, nullptr, st))) return rc;
       if (stop_after == 0) continue;
       if ((rc = table(KT_GC_TABLE, w.vg_img, g2m_ws, Ng, w.tg, st))) return rc;
       if ((rc = hidden<2>(KT_GC_HIDDEN, A1(e_g2m_img, GC_NKB), L, g2m_edge.w1, g2m_edge.b1, Eg, w.hid, w.tg, L, g2m_s, g2m_tr, L, g2m_r, st))) return rc;
@@ -423,20 +430,19 @@ struct GraphCastEngine : Engine {
       if ((rc = hidden<0>(KT_GC_HIDDEN, A2(vm0_img, w.agg_img), 2 * L, g2m_mesh.w1, g2m_mesh.b1, Nm, w.hid_m, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
       if ((rc = ln_gemm(KT_GC_LN, w.hid_m, g2m_mesh, Nm, vm0_f32, w.vm, w.vm_img, nullptr, st))) return rc;
       if ((rc = hidden<0>(KT_GC_HIDDEN, A1(w.vg_img, GC_NKB), L, g2m_grid.w1, g2m_grid.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
-      if ((rc = ln_gemm(KT_GC_LN, w.hid, g2m_grid, Ng, w.vg, w.vg, w.vg_img, nullptr, st))) return rc;
+      if ((rc = ln_gemm(KT_GC_LN, w.hid, g2m_grid, Ng, nullptr, nullptr, w.vg_img, nullptr, st, w.vg_img))) return rc;
       if (stop_after == 1) continue;
       // ---------------- processor
       bool stopped = false;
       for (int i = 0; i < cfg.layers; ++i) {
         const uint8_t* em_in_img = i ? w.em_img : e_mesh_img;
-        const float* em_in = i ? w.em : e_mesh_f32;
         if ((rc = table(KT_GC_TABLE, w.vm_img, proc_wsr[i], Nm, w.tm, st))) return rc;
         if ((rc = hidden<2>(KT_GC_HIDDEN, A1(em_in_img, GC_NKB), L, proc_edge[i].w1, proc_edge[i].b1, Em, w.hid_m, w.tm, 2 * L, mesh_s, w.tm + L,
                             2 * L, mesh_r, st))) return rc;
         // the edge latents are not read after the last layer: only the update image (for the aggregation) is produced there
         const bool last = i == cfg.layers - 1 && stop_after == 99;
-        if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_edge[i], Em, last ? nullptr : em_in, last ? nullptr : w.em, last ? nullptr : w.em_img,
-                          w.ym_img, st))) return rc;
+        if ((rc = ln_gemm(KT_GC_LN, w.hid_m, proc_edge[i], Em, nullptr, nullptr, last ? nullptr : w.em_img, w.ym_img, st,
+                          last ? nullptr : em_in_img))) return rc;
         if ((rc = segsum(KT_GC_AGG, w.ym_img, mesh_seg, w.agg_img, st))) return rc;
         if ((rc = hidden<0>(KT_GC_HIDDEN, A2(w.vm_img, w.agg_img), 2 * L, proc_node[i].w1, proc_node[i].b1, Nm, w.hid_m, nullptr, 0, nullptr, nullptr, 0,
                             nullptr, st))) return rc;
@@ -458,7 +464,7 @@ struct GraphCastEngine : Engine {
         a.img3 = w.yimg + 2 * seg; a.nkb3 = GC_NKB;
         if ((rc = hidden<0>(KT_GC_HIDDEN, a, 4 * L, m2g_grid.w1, m2g_grid.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
       }
-      if ((rc = ln_gemm(KT_GC_LN, w.hid, m2g_grid, Ng, w.vg, w.vg, w.vg_img, nullptr, st))) return rc;
+      if ((rc = ln_gemm(KT_GC_LN, w.hid, m2g_grid, Ng, nullptr, nullptr, w.vg_img, nullptr, st, w.vg_img))) return rc;
       if ((rc = range_scan(0, w.feat, img_bytes(Ng, GC_FEAT_KP / 64), st))) return rc;
       if (stop_after == 100) continue;
       if ((rc = hidden<0>(KT_GC_HIDDEN, A1(w.vg_img, GC_NKB), L, out_mlp.w1, out_mlp.b1, Ng, w.hid, nullptr, 0, nullptr, nullptr, 0, nullptr, st))) return rc;
@@ -488,11 +494,17 @@ struct GraphCastEngine : Engine {
     const Ws w = carve(ws_base);
     const float* src = nullptr; uint64_t n = 0;
     if (!strcmp(what, "range")) { src = range_dev; n = 8; if (!src) { set_error("range guard was never enabled"); return SKY_ERR_STATE; } }
-    else if (!strcmp(what, "vg")) { src = w.vg; n = (uint64_t)Ng * GC_L; }
     else if (!strcmp(what, "vm")) { src = w.vm; n = (uint64_t)Nm * GC_L; }
-    else if (!strcmp(what, "em")) { src = w.em; n = (uint64_t)Em * GC_L; }
     else if (!strcmp(what, "vm0")) { src = vm0_f32; n = (uint64_t)Nm * GC_L; }
-    else if (!strcmp(what, "e_mesh")) { src = e_mesh_f32; n = (uint64_t)Em * GC_L; }
+    else if (!strcmp(what, "vg") || !strcmp(what, "em") || !strcmp(what, "e_mesh")) {
+      // grid-node and mesh-edge latents exist only as fp16 operand images
+      const uint8_t* im = what[0] == 'v' ? w.vg_img : !strcmp(what, "em") ? w.em_img : e_mesh_img;
+      const long long rows = what[0] == 'v' ? Ng : Em;
+      if ((uint64_t)rows * GC_L > max_floats) { set_error("debug tensor '%s' needs %lld floats", what, rows * GC_L); return SKY_ERR_ARG; }
+      k_gc_img_to_rows<<<(unsigned)((rows * (GC_L / 8) + 255) / 256), 256, 0, st>>>(im, dst, rows);
+      SKY_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
     else { set_error("unknown debug tensor '%s'", what); return SKY_ERR_ARG; }
     if (n > max_floats) { set_error("debug tensor '%s' needs %llu floats", what, (unsigned long long)n); return SKY_ERR_ARG; }
     SKY_CUDA_OK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st));

@@ -154,21 +154,67 @@ struct EpiGcSiluImg {
   }
 };
 
-// y = LayerNorm(acc + bias) * gamma + beta over the full 512-wide row (one n-tile, n0 == 0), then any of
-//   xout[row] = (xin ? xin[row] : 0) + y      fp32 row-major (ld 512): the residual stream (xin may equal xout)
+// y = LayerNorm(acc + bias) * gamma + beta over the full 512-wide row, then any of
+//   xout[row] = residual + y                  fp32 row-major (ld 512); residual = xin (fp32 rows, may equal xout) or
+//                                             xin_img (the fp16 operand image of the stream, may equal img) or nothing
 //   img       = fp16 tile image of that sum   (the A operand of the next GEMM)
 //   yimg      = fp16 tile image of y itself   (what the aggregation sums: the update BEFORE the residual)
+// Grid-node and mesh-edge latents live ONLY as fp16 images (residual read from xin_img, sum formed in fp32, rounded once
+// into img): their consumers round to fp16 anyway, and the measured cost on the oracle is a tendency error of 7.95e-4
+// instead of 7.66e-4 over 16 layers (tests/test_graphcast_cpu.py); it saves 3 KB of HBM traffic per row and launch.
 // Structure follows Epi2F32Img (gemm2.cuh): statistics in the row-owner domain, then 32x32 blocks re-tiled through the
 // warp's patch so that every global access is a 128-bit access on a full 128-byte row segment.
+// kRes: residual source, a compile-time choice (a run-time branch per load serialised the loads and cost 10 - 50 % of the
+// kernel): 0 none, 1 fp32 rows (xin), 2 the stream's fp16 image (xin_img)
+template <int kRes>
 struct EpiGcLn {
   static constexpr bool kNeedsBias = true;
   const float* xin; float* xout; uint8_t* img; uint8_t* yimg;
   const float* bias; const float* gamma; const float* beta; float eps;
+  const uint8_t* xin_img = nullptr;
+  // residual values of the lane's eight (row, 4-column) pieces of the 32-column group at local column c: all eight
+  // loads are issued before any is used
+  __device__ __forceinline__ void residual8(const EpiCtx& e, int c, int rsub4, int c4, size_t rowoff, long long rows_left, bool on,
+                                            float4 (&x)[8]) const {
+    if constexpr (kRes == 1) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        x[it] = (on && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else if constexpr (kRes == 2) {
+      const int col = e.n0 + c + c4 * 4;
+      const uint8_t* base = xin_img + ((size_t)(e.row0 >> 7) * GC_NKB + (col >> 6)) * (size_t)G2_A_BYTES + (uint32_t)(e.row0 & 127) * 128 + (c4 & 1) * 8;
+      const uint32_t chunk = (uint32_t)(col & 63) >> 3;
+      uint2 u[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        u[it] = (on && rr < rows_left) ? *reinterpret_cast<const uint2*>(base + rr * 128 + ((chunk ^ (uint32_t)(rr & 7)) << 4)) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u[it].x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u[it].y));
+        x[it] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   template <int BN>
   __device__ void prefetch(const EpiCtx& e) const {
-    if (!xin) return;
+    if (kRes == 0) return;
     const long long row = e.row0 + e.lane;
     if (row >= e.M) return;
+    if (kRes == 2) {
+      const char* p = reinterpret_cast<const char*>(xin_img) + ((size_t)(e.row0 >> 7) * GC_NKB + (e.n0 >> 6)) * (size_t)G2_A_BYTES +
+                      ((uint32_t)(e.row0 & 127) + e.lane) * 128;
+#pragma unroll
+      for (int i = e.part; i < BN / 64; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * G2_A_BYTES));
+      return;
+    }
+    if (!xin) return;
     const char* p = reinterpret_cast<const char*>(xin + row * GC_L + e.n0);
 #pragma unroll
     for (int i = e.part; i < BN * 4 / 128; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
@@ -182,11 +228,7 @@ struct EpiGcLn {
     const size_t rowoff = (size_t)e.row0 * GC_L + e.n0 + c4 * 4;
     // residual rows of the first column group: requested before the statistics pass (they come from L2: prefetch())
     float4 xr[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + rsub4;
-      xr[it] = (xin && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + e.part * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    residual8(e, e.part * 32, rsub4, c4, rowoff, rows_left, true, xr);
     float s = 0.f, ss = 0.f;
     for (int g = e.part; g < NG; g += e.nparts) {
       float v[32];
@@ -244,15 +286,7 @@ struct EpiGcLn {
     for (int g = e.part; g < NG; g += e.nparts) {
       const int c = g * 32;
       float4 xn[8];   // next group's residual rows in flight while this group is normalised and stored
-      {
-        const bool more = g + e.nparts < NG;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub4;
-          xn[it] = (more && xin && rr < rows_left) ? *reinterpret_cast<const float4*>(xin + rowoff + (size_t)rr * GC_L + c + 32 * e.nparts)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+      residual8(e, c + 32 * e.nparts, rsub4, c4, rowoff, rows_left, g + e.nparts < NG, xn);
       {
         float v[32];
         acc.load32(c, v);
@@ -276,7 +310,7 @@ struct EpiGcLn {
           y.x = fmaf(fmaf(t.x + bs.x, rs[it], ns[it]), ga.x, be.x); y.y = fmaf(fmaf(t.y + bs.y, rs[it], ns[it]), ga.y, be.y);
           y.z = fmaf(fmaf(t.z + bs.z, rs[it], ns[it]), ga.z, be.z); y.w = fmaf(fmaf(t.w + bs.w, rs[it], ns[it]), ga.w, be.w);
           hy[u].x = pack_half2(y.x, y.y); hy[u].y = pack_half2(y.z, y.w);
-          y.x += xr[it].x; y.y += xr[it].y; y.z += xr[it].z; y.w += xr[it].w;
+          if (kRes) { y.x += xr[it].x; y.y += xr[it].y; y.z += xr[it].z; y.w += xr[it].w; }
           if (xout && rr < rows_left) *reinterpret_cast<float4*>(xout + rowoff + (size_t)rr * GC_L + c) = y;
           hx[u].x = pack_half2(y.x, y.y); hx[u].y = pack_half2(y.z, y.w);
         }
@@ -301,8 +335,10 @@ struct EpiGcLn {
         }
       }
       __syncwarp();
+      if (kRes) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) xr[it] = xn[it];
+        for (int it = 0; it < 8; ++it) xr[it] = xn[it];
+      }
     }
   }
 };
@@ -389,6 +425,19 @@ __global__ void k_gc_m2g_feat(const float* __restrict__ src, float* __restrict__
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (g < ng) v = *reinterpret_cast<const float4*>(src + (k * ng + g) * 4);
   *reinterpret_cast<float4*>(dst + i * 4) = v;
+}
+
+// test tap: fp16 tile image (GC_NKB k-blocks per row tile) -> fp32 row-major (rows, 512)
+__global__ void k_gc_img_to_rows(const uint8_t* __restrict__ img, float* __restrict__ out, long long rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-column chunk each
+  if (idx >= rows * (GC_L / 8)) return;
+  const long long r = idx / (GC_L / 8); const int j = (int)(idx % (GC_L / 8));
+  const uint4 p = *reinterpret_cast<const uint4*>(img + (size_t)(r >> 7) * GC_NKB * G2_A_BYTES + (size_t)(j >> 3) * G2_A_BYTES +
+                                                  sw128_offset((uint32_t)(r & 127), (uint32_t)(j & 7)));
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  add_h8(v, p);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[r * GC_L + j * 8 + k] = v[k];
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -115,7 +115,8 @@ def graphcast_counts(cfg, graph=None) -> dict:
 def _graphcast_schedule(cfg, n):
     """The engine's per-step GEMM schedule (csrc/graphcast_engine.cu::step) as (family, rows, K, N, bytes per row):
     hidden GEMMs read their A operand image(s) (2 B per element) and write the 512-wide hidden image; LayerNorm GEMMs read
-    the hidden image and write / read-modify-write the residual stream (fp32) and the operand images listed."""
+    the hidden image, read the residual (fp32 rows for mesh nodes, the stream's own fp16 image for grid nodes and mesh edges) and
+    write the operand images listed."""
     L, F = cfg.latent, 192
     Ng, Nm, Em, Eg = n["Ng"], n["Nm"], n["Em"], n["Eg"]
     s = []
@@ -123,17 +124,20 @@ def _graphcast_schedule(cfg, n):
     # (1 GB) is read from HBM per gathered row
     hid = lambda rows, K, grid_tab=0, mesh_tab=0: s.append(("gc_hidden", rows, K, L, 2.0 * K + 2.0 * L + grid_tab * 2.0 * L
                                                             + mesh_tab * Nm * 2.0 * L / rows))
-    ln = lambda rows, rmw, img, yimg: s.append(("gc_ln", rows, L, L, 2.0 * L + (8.0 * L if rmw == 2 else 4.0 * L if rmw == 1 else 0.0)
+    # residual: 0 none, 2 fp32 rows read + written (mesh nodes), 3 read from the stream's fp16 image (grid nodes, mesh edges)
+    ln = lambda rows, res, img, yimg: s.append(("gc_ln", rows, L, L, 2.0 * L + (8.0 * L if res == 2 else 2.0 * L if res == 3 else 0.0)
                                                 + 2.0 * L * (img + yimg)))
     tab = lambda rows, N: s.append(("gc_table", rows, L, N, 2.0 * L + 2.0 * N))
-    hid(Ng, F); ln(Ng, 1, 1, 0)                                   # grid embedding
+    hid(Ng, F); ln(Ng, 0, 1, 0)                                   # grid embedding
     tab(Ng, L); hid(Eg, L, grid_tab=1, mesh_tab=1); ln(Eg, 0, 0, 1)             # grid2mesh edges
     hid(Nm, 2 * L); ln(Nm, 2, 1, 0)                               # mesh nodes
-    hid(Ng, L); ln(Ng, 2, 1, 0)                                   # grid nodes
-    for _ in range(cfg.layers):
-        tab(Nm, 2 * L); hid(Em, L, mesh_tab=2); ln(Em, 2, 1, 1); hid(Nm, 2 * L); ln(Nm, 2, 1, 0)
+    hid(Ng, L); ln(Ng, 3, 1, 0)                                   # grid nodes
+    for i in range(cfg.layers):
+        tab(Nm, 2 * L); hid(Em, L, mesh_tab=2)
+        ln(Em, 3, 1, 1) if i < cfg.layers - 1 else ln(Em, 0, 0, 1)   # the last layer's edge latents are never read
+        hid(Nm, 2 * L); ln(Nm, 2, 1, 0)
     tab(Nm, L); tab(Ng, L); hid(3 * Ng, L, grid_tab=1, mesh_tab=1); ln(3 * Ng, 0, 0, 1)   # mesh2grid edges
-    hid(Ng, 4 * L); ln(Ng, 2, 1, 0)                               # grid update ([v | e0 | e1 | e2]: read as 4 images)
+    hid(Ng, 4 * L); ln(Ng, 3, 1, 0)                               # grid update ([v | e0 | e1 | e2]: read as 4 images)
     hid(Ng, L)                                                    # output head, first layer
     return s
 
