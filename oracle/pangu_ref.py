@@ -83,7 +83,7 @@ class PanguRef:
 
     # -- operand rounding hooks -----------------------------------------------------------
     def _q(self, t):
-        if self.emulate == "fp16":
+        if self.emulate in ("fp16", "fp16s"):
             return t.to(torch.float16).to(self.dtype)
         if self.emulate == "bf16":
             return t.to(torch.bfloat16).to(self.dtype)
@@ -156,10 +156,13 @@ class PanguRef:
         if roll:
             y = torch.roll(y, shifts=(wz // 2, wh // 2, ww // 2), dims=(0, 1, 2))
         y = y[:, :H]
-        x = x + F.layer_norm(y, (C,), w[p + "ln1.g"], w[p + "ln1.b"], cfg.ln_eps)
+        # emulate="fp16s": like "fp16", and the residual stream itself is kept in half between the sub-layers (the engine
+        # stores the token stream only as its fp16 operand image: sum in fp32, one rounding per residual add)
+        qs = (lambda t: t.to(torch.float16).to(self.dtype)) if self.emulate == "fp16s" else (lambda t: t)
+        x = qs(x + F.layer_norm(y, (C,), w[p + "ln1.g"], w[p + "ln1.b"], cfg.ln_eps))
         hdn = F.gelu(self._linear(x, w[p + "fc1.w"], w[p + "fc1.b"]))
         y = self._linear(self._q(hdn), w[p + "fc2.w"], w[p + "fc2.b"])
-        x = x + F.layer_norm(y, (C,), w[p + "ln2.g"], w[p + "ln2.b"], cfg.ln_eps)
+        x = qs(x + F.layer_norm(y, (C,), w[p + "ln2.g"], w[p + "ln2.b"], cfg.ln_eps))
         return x
 
     def layer(self, x, li):

@@ -346,11 +346,15 @@ struct Epi2F16 {
 //   kResidual: x += y, else x = y  (bias, if any, is applied when !kLn as well)
 // Global traffic is 128-bit: lane -> (row = it*4 + lane/8, float4 column group = lane%8), i.e.
 // eight lanes cover one 128-byte row segment.  bias / gamma / beta come from shared memory.
-template <bool kLn, bool kResidual>
+// kImgStream: the rows exist ONLY as their fp16 operand image — the residual is read from `img` (in place), the sum is formed in
+// fp32 and rounded once back into `img`; nothing is read from or written to x.  Round 2 (late): on the oracle an fp16-only
+// residual stream moves the Pangu step error from 5.3e-4 to 5.9e-4 (tests/test_oracle_cpu.py) and removes 8 of the 12 bytes
+// per token and feature that the projection / MLP epilogues move through HBM.
+template <bool kLn, bool kResidual, bool kImgStream = false>
 struct Epi2F32Img {
   static constexpr bool kNeedsBias = kLn;
-  float* x; int ldx;            // fp32 row-major
-  uint8_t* img; int nkb;        // fp16 image of the same rows (may be null)
+  float* x; int ldx;            // fp32 row-major (unused when kImgStream)
+  uint8_t* img; int nkb;        // fp16 image of the same rows (may be null unless kImgStream)
   const float* bias; const float* gamma; const float* beta; float eps;  // bias may be null when !kLn
 #ifdef SKY_EXPERIMENTS
   int exp = 0;  // timing experiments only (results invalid): 1 = no residual loads, 2 = no fp32 stores, 4 = no image stores
@@ -360,11 +364,28 @@ struct Epi2F32Img {
   // Pull this warp's residual rows into L2 ahead of time.  A register-destination prefetch does
   // not work here: tcgen05.wait::ld also waits for the thread's outstanding global loads, so
   // every TMEM read in run() would expose the full HBM latency (profiles/r1_mlp.md).
+  // four residual values of row (row0 + rr) at tile column n0 + c + 4 * c4, read from the fp16 image
+  __device__ __forceinline__ uint2 img_res_raw(const EpiCtx& e, int rr, int c, int c4) const {
+    const int col = e.n0 + c + c4 * 4;
+    return *reinterpret_cast<const uint2*>(img + ((size_t)(e.row0 >> 7) * nkb + (col >> 6)) * (size_t)G2_A_BYTES +
+                                           ((uint32_t)(e.row0 & 127) + rr) * 128 + ((((uint32_t)(col & 63) >> 3) ^ (uint32_t)(rr & 7)) << 4) + (c4 & 1) * 8);
+  }
+  static __device__ __forceinline__ float4 h4_to_f4(const uint2& u) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
   template <int BN>
   __device__ void prefetch(const EpiCtx& e) const {
     if (!kResidual) return;
     const long long row = e.row0 + e.lane;
     if (row >= e.M) return;
+    if (kImgStream) {
+      const char* p = reinterpret_cast<const char*>(img) + ((size_t)(e.row0 >> 7) * nkb + (e.n0 >> 6)) * (size_t)G2_A_BYTES +
+                      ((uint32_t)(e.row0 & 127) + e.lane) * 128;
+#pragma unroll
+      for (int i = e.part; i < BN / 64; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * G2_A_BYTES));
+      return;
+    }
     const char* p = reinterpret_cast<const char*>(x + row * ldx + e.n0);
 #pragma unroll
     for (int i = e.part; i < BN * 4 / 128; i += e.nparts) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
@@ -386,11 +407,22 @@ struct Epi2F32Img {
     float* xp = x + e.row0 * ldx + e.n0 + c4 * 4;
     const bool ld_on = kResidual && !(exp & 1);
     float4 xin[8];
+    if constexpr (kImgStream) {
+      uint2 raw[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + rsub4;
-      xin[it] = (kPrefetch && ld_on && rr < rows_left && e.part < NG) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
-                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        raw[it] = (kPrefetch && ld_on && rr < rows_left && e.part < NG) ? img_res_raw(e, rr, e.part * 32, c4) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) xin[it] = h4_to_f4(raw[it]);
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub4;
+        xin[it] = (kPrefetch && ld_on && rr < rows_left && e.part < NG) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + e.part * 32)
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     float rs[8], ns[8];   // rstd and -mean*rstd of row it*4 + rsub4
 #pragma unroll
@@ -435,10 +467,21 @@ struct Epi2F32Img {
     for (int g = e.part; g < NG; g += e.nparts) {
       const int c = g * 32;
       if (!kPrefetch && kResidual) {
+        if constexpr (kImgStream) {
+          uint2 raw[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub4;
-          xin[it] = (ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub4;
+            raw[it] = (ld_on && rr < rows_left) ? img_res_raw(e, rr, c, c4) : make_uint2(0u, 0u);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) xin[it] = h4_to_f4(raw[it]);
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub4;
+            xin[it] = (ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       {
@@ -458,11 +501,22 @@ struct Epi2F32Img {
       const bool more = g + e.nparts < NG;
       float4 xnext[kPrefetch ? 8 : 1];
       if constexpr (kResidual && kPrefetch) {
+        if constexpr (kImgStream) {
+          uint2 raw[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rsub4;
-          xnext[it] = (more && ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c + 32 * e.nparts)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub4;
+            raw[it] = (more && ld_on && rr < rows_left) ? img_res_raw(e, rr, c + 32 * e.nparts, c4) : make_uint2(0u, 0u);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) xnext[it] = h4_to_f4(raw[it]);
+        } else {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub4;
+            xnext[it] = (more && ld_on && rr < rows_left) ? *reinterpret_cast<const float4*>(xp + (size_t)rr * ldx + c + 32 * e.nparts)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       const int col = e.n0 + c;
@@ -480,7 +534,7 @@ struct Epi2F32Img {
           y.x = fmaf(fmaf(t.x + bs.x, rs[it], ns[it]), ga.x, be.x); y.y = fmaf(fmaf(t.y + bs.y, rs[it], ns[it]), ga.y, be.y);
           y.z = fmaf(fmaf(t.z + bs.z, rs[it], ns[it]), ga.z, be.z); y.w = fmaf(fmaf(t.w + bs.w, rs[it], ns[it]), ga.w, be.w);
           if (kResidual) { y.x += xin[it].x; y.y += xin[it].y; y.z += xin[it].z; y.w += xin[it].w; }
-          if (rr < rows_left && !(exp & 2)) *reinterpret_cast<float4*>(xp + (size_t)rr * ldx + c) = y;
+          if (!kImgStream && rr < rows_left && !(exp & 2)) *reinterpret_cast<float4*>(xp + (size_t)rr * ldx + c) = y;
           h[u].x = pack_half2(y.x, y.y); h[u].y = pack_half2(y.z, y.w);
         }
         if (ibase && !(exp & 4)) {
@@ -503,8 +557,10 @@ struct Epi2F32Img {
   }
 };
 
-// post-norm residual of the attention projection and of the MLP
-using EpiLnRes = Epi2F32Img<true, true>;
+// post-norm residual of the attention projection and of the MLP: fp32 row-major token stream (EpiLnRes) or the stream kept
+// only as its fp16 operand image (EpiLnResImg); the engine picks one per handle (pangu_engine.cu, "fp32_stream")
+using EpiLnRes = Epi2F32Img<true, true, false>;
+using EpiLnResImg = Epi2F32Img<true, true, true>;
 
 // up-sample linear1 (N = 4C as (hs, ws, C); one n-tile = one sub-position): LayerNorm over
 // the C features of the tile, written as fp16 image rows of the FINE token

@@ -49,10 +49,10 @@ struct MlpCfg {
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
-template <int C>
+template <int C, class EpiT = EpiLnRes>
 __global__ void __launch_bounds__(352, 1)
 k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
-            const EpiLnRes epi,   // x (fp32), xh out image, b2, gamma, beta
+            const EpiT epi,   // x (fp32), xh out image, b2, gamma, beta
             const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
             const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
             const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg, int expflags) {
@@ -297,14 +297,14 @@ k_mlp_fused(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   }
 }
 
-template <int C>
-int launch_mlp_fused(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W1img,
+template <int C, class EpiT = EpiLnRes>
+int launch_mlp_fused(const uint8_t* xh_in, const EpiT& epi, const uint8_t* W1img,
                      const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
   static int dbg_runs = 0;
   if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 256 * 8);
   using Cfg = MlpCfg<C>;
-  auto kern = k_mlp_fused<C>;
+  auto kern = k_mlp_fused<C, EpiT>;
   static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
   if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);

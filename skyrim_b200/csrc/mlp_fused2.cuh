@@ -64,10 +64,10 @@ struct Mlp2Cfg {
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
-template <int C>
+template <int C, class EpiT = EpiLnRes>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
-                 const EpiLnRes epi,   // x (fp32), xh out image, b2, gamma, beta
+                 const EpiT epi,   // x (fp32), xh out image, b2, gamma, beta
                  const uint8_t* __restrict__ W1img,  // [4C/HC][C/64][HC x 128B]
                  const uint8_t* __restrict__ W2img,  // [1][4C/64][C x 128B]
                  const float* __restrict__ b1, long long M, int num_m_tiles, long long* dbg_in) {
@@ -341,8 +341,8 @@ k_mlp_fused_pair(const uint8_t* __restrict__ xh_in,  // A image of x (tokens, C)
   }
 }
 
-template <int C>
-int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiLnRes& epi, const uint8_t* W1img,
+template <int C, class EpiT = EpiLnRes>
+int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiT& epi, const uint8_t* W1img,
                           const uint8_t* W2img, const float* b1, long long M, int num_sms, cudaStream_t st) {
   static long long* dbg = nullptr;
 #ifdef SKY_EXPERIMENTS
@@ -350,7 +350,7 @@ int launch_mlp_fused_pair(const uint8_t* xh_in, const EpiLnRes& epi, const uint8
   if (getenv("SKY_MLP_DBG") && !dbg) cudaMallocManaged(&dbg, 256 * 8);
 #endif
   using Cfg = Mlp2Cfg<C>;
-  auto kern = k_mlp_fused_pair<C>;
+  auto kern = k_mlp_fused_pair<C, EpiT>;
   static std::atomic<uint64_t> configured{0};   // one bit per device: the attribute is per (function, device)
   if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES)) return rc;
   const int tiles = (int)((M + 127) / 128);
