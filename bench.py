@@ -463,8 +463,8 @@ def bench_model(model: str, M: int, steps: int, warmup: int, d: Dist, e2e: bool 
 
 def _traffic(family):
     """DRAM bytes per launch of a kernel family from the committed `ncu --set full` capture of this round's kernels
-    (profiles/r2_traffic.json, provenance and kernel names inside); None when no capture covers the family."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    (profiles/r2f_traffic.json, provenance and kernel names inside); None when no capture covers the family."""
+    for name in ("r2f_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         try:
             with open(p) as f:

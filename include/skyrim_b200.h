@@ -129,7 +129,9 @@ SKY_API int sky_toa_radiation(float* out, int32_t nlat, int32_t nlon, double uni
 SKY_API int sky_model_debug_copy(sky_model_t* m, const char* what, float* dst, uint64_t max_floats, void* workspace,
                          int32_t batch, void* stream);
 
-/* Debug switches of a handle (tests only; never read from the environment): "stop_after" = n makes step() return after
+/* Switches of a handle (never read from the environment).  "fp32_stream" = 1 (Pangu) keeps the token stream as fp32 rows beside
+ * its fp16 operand image instead of the default image-only stream: 1.1 ms per step slower, one rounding per residual add less
+ * (DESIGN.md section 3).  Test taps: "stop_after" = n makes step() return after
  * stage n (0 embed, 1 layer0, 2 down, 3 layer1, 4 layer2, 5 up, 6 layer3; 99 = run the whole step) so that
  * sky_model_debug_copy can read the intermediate token buffers. */
 SKY_API int sky_model_debug_set(sky_model_t* m, const char* key, int64_t value);

@@ -453,8 +453,25 @@ struct Epi2F32Img {
         }
         asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(32 * e.nparts) : "memory");   // the patches are reused below
       }
-      const float mean = s / BN;
-      const float rstd = rsqrtf(fmaxf(ss / BN - mean * mean, 0.f) + eps);
+      float width = (float)BN;
+      if (e.x_own_bar) {
+        // column-split CTA pair (gemm_split.cuh): the other half of these rows is in the peer CTA — post this CTA's sums into
+        // the peer's slot (st.async completes the peer's mbarrier transaction), wait for the peer's, add
+        if (e.part == 0) {
+          if (e.lane == 0) mbar_arrive_expect_tx(e.x_own_bar, 32 * 8);
+          __syncwarp();
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(e.x_peer_stat + e.lane * 8),
+                       "f"(s), "f"(ss), "r"(e.x_peer_bar)
+                       : "memory");
+        }
+        mbar_wait_cluster(e.x_own_bar, e.x_parity);
+        float ps, pss;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(e.x_own_stat + e.lane * 8));
+        s += ps; ss += pss;
+        width = (float)(2 * BN);
+      }
+      const float mean = s / width;
+      const float rstd = rsqrtf(fmaxf(ss / width - mean * mean, 0.f) + eps);
       const float nmr = -mean * rstd;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {

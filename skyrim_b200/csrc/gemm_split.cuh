@@ -1,6 +1,7 @@
-// Column-split CTA pairs for GEMMs whose epilogue needs whole 512-wide rows (GraphCast: second MLP layer + LayerNorm):
+// Column-split CTA pairs for GEMMs whose epilogue needs whole rows wider than half of TMEM (GraphCast: second MLP layer +
+// LayerNorm over 512 columns; Pangu: attention projection + LayerNorm at C = 384):
 //
-//     D[M, 512] = A[M, K] W[512, K]^T  ->  epilogue over full rows
+//     D[M, 2 BLOCK_N] = A[M, K] W[2 BLOCK_N, K]^T  ->  epilogue over full rows
 //
 // k_gemm2 with BLOCK_N = 512 fills all 512 TMEM columns with ONE accumulator: the epilogue of a tile (residual read-modify-
 // write of 2 KB per row, HBM bound) and the main loop of the next one (640 KB of L2 -> SM traffic through a 2-stage ring)
@@ -16,11 +17,11 @@
 
 namespace sky {
 
-template <class Epi, int EPI_WARPS>
+template <class Epi, int EPI_WARPS, int BLOCK_N = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EPI_WARPS + 2) * 32, 1)
 k_gemm_split(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, long long M, int num_kb, int num_m_tiles) {
-  constexpr int BLOCK_N = 256;
   using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
+  static_assert(2 * BLOCK_N <= 512, "two accumulators per CTA");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* patches = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -138,13 +139,14 @@ k_gemm_split(const AImage A, const Epi epi, const uint8_t* __restrict__ Wimg, lo
   }
 }
 
-// Wimg: [2][K/64][256 rows x 128 B] (weight packed with BLOCK_N = 256)
-template <class Epi, int EPI_WARPS>
+// Wimg: [2][K/64][BLOCK_N rows x 128 B] (weight packed with BLOCK_N = half of the row width: 256 for GraphCast's 512-wide
+// latents, 192 for Pangu's C = 384 projection)
+template <class Epi, int EPI_WARPS, int BLOCK_N = 256>
 int launch_gemm_split(const AImage& A, const Epi& epi, const uint8_t* Wimg, long long M, int Kp, int num_sms, cudaStream_t st) {
-  using Cfg = G2Cfg<256, EPI_WARPS>;
+  using Cfg = G2Cfg<BLOCK_N, EPI_WARPS>;
   constexpr int SMEM = Cfg::SMEM_BYTES + 2048;
   static_assert(SMEM <= 232448, "smem budget");
-  auto kern = k_gemm_split<Epi, EPI_WARPS>;
+  auto kern = k_gemm_split<Epi, EPI_WARPS, BLOCK_N>;
   static std::atomic<uint64_t> configured{0};
   if (int rc = smem_opt_in(configured, reinterpret_cast<const void*>(kern), SMEM)) return rc;
   const int num_m_tiles = (int)((M + G2_BLOCK_M - 1) / G2_BLOCK_M);

@@ -18,6 +18,7 @@
 #include "gemm_tc.cuh"
 #include "mlp_fused2.cuh"
 #include "gemm_pair.cuh"
+#include "gemm_split.cuh"
 #ifdef SKY_EXPERIMENTS
 // development build only (libskyrim_b200_dev.so): CUDA-core reference GEMMs under the same epilogues, the single-CTA
 // kernel variants and the result-invalidating timing switches.  None of this is compiled into the product library.
@@ -138,6 +139,7 @@ struct GemmW {
 };
 struct BlockW {
   GemmW qkv, proj, fc1, fc2;
+  GemmW proj_s;  // C = 384: the projection packed in 192-row halves for the column-split pair kernel (gemm_split.cuh)
   GemmW fc1f;  // fc1 packed in hidden-chunk tiles for the fused MLP kernel
   const float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   __half* bias_tab;  // (n_type, heads, 3312), fp16, pre-scaled by log2 e
@@ -152,6 +154,7 @@ struct PanguEngine : Engine {
   // per token and feature of the projection / MLP epilogues disappear; step error 5.8e-4 instead of 5.1e-4 at 721x1440),
   // false = fp32 rows beside the image (round-1 / early round-2 data flow; for weights whose error margin is tighter)
   bool img_stream = true;
+  bool proj_split = true;   // C = 384 projection on column-split CTA pairs ("proj_split" 0: one 384-column accumulator)
   // fused MLP on CTA pairs (cta_group::2) per channel width; SKY_MLP=1cta|pair192|pair384 selects for A/B timing
   bool mlp_pair192 = true, mlp_pair384 = true;
   bool qkv_pair = true;     // SKY_QKV=1cta selects k_gemm2 for the QKV projection (A/B timing)
@@ -264,6 +267,7 @@ struct PanguEngine : Engine {
         auto N = [&](const char* s) { snprintf(nm, sizeof nm, "layer%d.block%d.%s", li, bi, s); return nm; };
         if ((rc = pack(b.qkv, N("qkv.w"), 3 * c, c, 192, false, st))) return rc;
         if ((rc = pack(b.proj, N("proj.w"), c, c, c, false, st))) return rc;
+        if (c == 384 && (rc = pack(b.proj_s, N("proj.w"), c, c, 192, false, st))) return rc;
         if ((rc = pack(b.fc1, N("fc1.w"), 4 * c, c, 192, false, st))) return rc;
         if ((rc = pack(b.fc2, N("fc2.w"), c, 4 * c, c, false, st))) return rc;
 #ifdef SKY_EXPERIMENTS
@@ -427,8 +431,17 @@ struct PanguEngine : Engine {
 #ifdef SKY_EXPERIMENTS
       e.exp = exp_ln;
 #endif
-      rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
-                    : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
+      if (C == 384 && proj_split && !use_ref) {
+        // one 384-column accumulator cannot be double buffered in TMEM: the two CTAs of a cluster take 192 columns each of the
+        // same 128 rows (epilogue of tile i under the main loop of tile i + 1), LayerNorm statistics cross through DSMEM
+        prof_begin(KT_PROJ, st);
+        count_launch();
+        rc = launch_gemm_split<ELn, 8, 192>(A, e, b.proj_s.img, R, C, num_sms, st);
+        prof_end(KT_PROJ, st);
+      } else {
+        rc = C == 192 ? gemm2<192, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st)
+                      : gemm2<384, 8>(KT_PROJ, A, e, b.proj, R, ws.scratch, st);
+      }
       if (rc) return rc;
     }
 #ifdef SKY_EXPERIMENTS
@@ -554,6 +567,7 @@ struct PanguEngine : Engine {
 
   int debug_set(const char* key, long long value) override {
     if (!strcmp(key, "fp32_stream")) { img_stream = value == 0; drop_graphs(); return 0; }
+    if (!strcmp(key, "proj_split")) { proj_split = value != 0; drop_graphs(); return 0; }
     return Engine::debug_set(key, value);
   }
 

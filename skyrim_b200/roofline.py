@@ -34,12 +34,14 @@ def pangu_flops(cfg: PanguConfig) -> dict:
 
 
 def pangu_bytes(cfg: PanguConfig) -> dict:
-    """Mandatory HBM bytes per 6-h step and kernel family for the data flow of DESIGN.md section 3 (fp32 residual stream x,
-    fp16 operand images xh; weights stay in L2 and are not counted).  Per token and feature:
+    """Mandatory HBM bytes per 6-h step and kernel family for the DEFAULT data flow of DESIGN.md section 3 (the token stream
+    exists only as its fp16 operand image xh; weights stay in L2 and are not counted).  Per token and feature:
       qkv    read xh 2 B, write q|k|v window images 3 x 2 B (padded tokens included)
       attn   read q|k|v 6 B, write the projection's operand image 2 B
-      proj   read operand image 2 B, residual x read 4 B + write 4 B, next operand image 2 B
-      mlp    read xh 2 B, x read + write 8 B, xh write 2 B (the 4C hidden activation never leaves the SM)"""
+      proj   read operand image 2 B, residual read from xh 2 B, xh written in place 2 B
+      mlp    read xh 2 B (operand; the epilogue re-reads the same image as the residual: an L2 hit, ncu profiles/r2f_traffic.json),
+             xh written in place 2 B (the 4C hidden activation never leaves the SM)
+    (with the fp32 token stream, "fp32_stream", proj and mlp move 12 B)"""
     C = cfg.dim
     HW = cfg.H * cfg.W
     T1, T2 = cfg.Z * HW, cfg.Z * cfg.H2 * cfg.W2
@@ -50,13 +52,13 @@ def pangu_bytes(cfg: PanguConfig) -> dict:
         c, T, rows = (C, T1, nwin1 * WIN_TOK) if li in (0, 3) else (2 * C, T2, nwin2 * WIN_TOK)
         b["qkv"] += depth * (2.0 * T * c + 6.0 * rows * c)
         b["attn"] += depth * (6.0 * rows * c + 2.0 * T * c)
-        b["proj"] += depth * 12.0 * T * c
-        b["mlp"] += depth * 12.0 * T * c
+        b["proj"] += depth * 6.0 * T * c
+        b["mlp"] += depth * 4.0 * T * c
     state = float(pangu_state_bytes(cfg))
     b["embed"] = state + T1 * C * (4.0 + 2.0)                  # state in; x (fp32) + operand image out
     b["recover"] = 2.0 * T1 * C * 2.0 + state                  # concat(skip, x) images in; state out
-    b["down"] = T1 * C * 4.0 + T2 * 4 * C * 2.0 * 2 + T2 * 2 * C * (4.0 + 2.0)   # x in, merged image out + in, x2 + image out
-    b["up"] = T2 * 2 * C * 2.0 + T1 * C * 2.0 * 2 + T1 * C * (4.0 + 2.0)       # image in, shuffled image out + in, x1 + image out
+    b["down"] = T1 * C * 2.0 + T2 * 4 * C * 2.0 * 2 + T2 * 2 * C * 2.0           # image in, merged image out + in, image out
+    b["up"] = T2 * 2 * C * 2.0 + T1 * C * 2.0 * 2 + T1 * C * 2.0                 # image in, shuffled image out + in, image out
     b["total"] = sum(b.values())
     return b
 

@@ -182,6 +182,6 @@ def test_bench_traffic_lookup_and_roofline_tables():
     fams, fl, by = mod.family_roofline("pangu", pangu_full(), 1, {"mlp": 5.0, "attn": 2.0, "embed": 0.3},
                                        dict(hbm=6572.0, tensor_sustained=1431.0))
     assert fams["mlp"]["bound"] == "tensor" and fams["attn"]["bound"] == "hbm" and 0.5 < fams["attn"]["frac"] < 0.8
-    assert abs(fl["total"] - 8.26e12) < 0.2e12 and 40e9 < by["total"] < 50e9
+    assert abs(fl["total"] - 8.26e12) < 0.2e12 and 28e9 < by["total"] < 36e9   # image-only token stream (12 -> 6 B in proj / mlp)
     fams, fl, by = mod.family_roofline("sfno", sfno_full(), 1, {"sfno_mlp": 5.0}, dict(hbm=6572.0, tensor_sustained=1431.0))
     assert "sfno_mlp" in fams and 2e12 < fl["total"] < 6e12

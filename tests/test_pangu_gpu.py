@@ -208,3 +208,28 @@ def test_cta_pair_kernels_agree_with_single_cta_kernels(small):
     assert rel_err_per_channel(yp, ys).max() < 2e-4, rel_err_per_channel(yp, ys).max()
     assert rel_err_per_channel(yp, yr).max() < TOL and rel_err_per_channel(ys, yr).max() < TOL
     pair.close(); single.close()
+
+
+def test_projection_on_column_split_pairs_matches_single_accumulator(small):
+    """C = 384 projections run on column-split CTA pairs (gemm_split.cuh: 2 x 192 columns, LayerNorm statistics exchanged
+    through distributed shared memory); the one-accumulator k_gemm2<.., 384> path differs in the summation order of the row
+    statistics — 1e-7 differences that the fp16 rounding of the operand images turns into occasional one-ulp flips, which 16
+    layers spread to a few 1e-4 per channel (both variants meet the oracle parity on their own).  121 x 384: 48 row tiles at
+    C = 384 on 74 CTA pairs here, 1,024 at the BASELINE shape (tests/test_fullsize_gpu.py runs the split path too)."""
+    from oracle.pangu_ref import PanguRef, rel_err_per_channel
+    from skyrim_b200.config import PANGU_CHANNELS, pangu_small
+    from skyrim_b200.weights import make_pangu_weights, synthetic_state
+    cfg = pangu_small(121, 384)
+    w = make_pangu_weights(cfg, 0)
+    x0 = torch.from_numpy(synthetic_state(PANGU_CHANNELS, cfg.nlat, cfg.nlon, 0))[None].cuda()
+    eng = _engine(cfg, w)
+    a = eng.step(x0).clone()
+    eng.debug_set("proj_split", 0)
+    b = eng.step(x0)
+    e = rel_err_per_channel(a[0].cpu().numpy(), b[0].cpu().numpy())
+    print(f"projection split vs single accumulator: max per-channel difference {e.max():.2e}")
+    ref = PanguRef(cfg, w).step(x0[0].cpu().numpy()).numpy()
+    ea, eb = rel_err_per_channel(a[0].cpu().numpy(), ref), rel_err_per_channel(b[0].cpu().numpy(), ref)
+    print(f"    against the oracle: split {ea.max():.3e}, single accumulator {eb.max():.3e}")
+    assert e.max() < 1e-3 and ea.max() < TOL and eb.max() < TOL, (e.max(), ea.max(), eb.max())
+    eng.close()
