@@ -176,7 +176,7 @@ def test_bench_traffic_lookup_and_roofline_tables():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     t, src = mod._traffic("mlp")
-    assert isinstance(t, int) and 3e8 < t < 2e9 and src.startswith("profiles/")   # bytes per launch of the fused MLP
+    assert isinstance(t, int) and 1e8 < t < 2e9 and src.startswith("profiles/")   # bytes per launch of the fused MLP (196 MB with the image-only token stream)
     assert mod._traffic("no-such-family") == (None, None)
     from skyrim_b200.config import pangu_full, sfno_full
     fams, fl, by = mod.family_roofline("pangu", pangu_full(), 1, {"mlp": 5.0, "attn": 2.0, "embed": 0.3},
