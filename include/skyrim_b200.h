@@ -71,6 +71,17 @@ typedef struct {
   int32_t dt_hours;        /* 6 */
   float ln_eps;            /* 1e-5 */
 } sky_graphcast_config_t;
+/* Arena entries of a GraphCast model (all fp32; index tables hold exact integers < 2^24):
+ *   norm.mean, norm.std, norm.diff_std (n_state each), static.fields (n_static, nlat, nlon)
+ *   <mlp>.w1 (512, fan_in), .b1 (512), .w2 (fan_out, 512), .b2 (fan_out), .ln.g / .ln.b (fan_out; not for dec.out) for <mlp> in
+ *     enc.grid_embed (184), enc.mesh_embed (3), enc.g2m_edge_embed (4), enc.g2m_edge (1536), enc.g2m_mesh (1024), enc.g2m_grid (512),
+ *     proc.edge_embed (4), proc<i>.edge (1536), proc<i>.node (1024) for i < layers, dec.m2g_edge_embed (4), dec.m2g_edge (1536),
+ *     dec.m2g_grid (1024), dec.out (512 -> n_state)          [first-layer input order: edge | sender | receiver, node | aggregate]
+ *   graph.mesh.senders / .receivers (n_mesh_edges, sorted by receiver), graph.mesh.ptr (n_mesh + 1), graph.mesh.edge_feat (n_mesh_edges, 4),
+ *   graph.mesh.node_feat (n_mesh, 3), graph.g2m.senders / .receivers / .ptr / .edge_feat (same, grid -> mesh),
+ *   graph.m2g.senders (3 * nlat * nlon, k-major: edge k of grid point g at k * n_grid + g), graph.m2g.edge_feat (3 * n_grid, 4),
+ *   graph.grid.coslat (nlat), graph.grid.sinlon / .coslon (nlon)
+ * (skyrim_b200/weights.py::graphcast_param_shapes, skyrim_b200/icomesh.py::graph_arena_entries build exactly this set). */
 
 /* one named fp32 tensor inside a flat weight arena */
 typedef struct {

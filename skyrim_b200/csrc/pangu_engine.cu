@@ -499,11 +499,11 @@ struct PanguEngine : Engine {
     {
       long long M = (long long)B * nzt * HW;
       ProdEmbedUpper p{x_in, mean, stdv, cfg.nlat, cfg.nlon, cfg.n_levels, 5, nch, g1.H, g1.W, nzt, M};
-      EpiStoreF32 e{ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW, ws.skiph, C / 64};
+      EpiStoreF32 e{img_stream ? nullptr : ws.x1, C, embed_u_b, M, g1.T, HW, 1, (long long)nzt * HW, ws.skiph, C / 64};
       if ((rc = gemm_prod<192>(KT_EMBED, p, e, embed_u, M, ws.scratch, st))) return rc;
       long long Ms = (long long)B * HW;
       ProdEmbedSurf ps{x_in, masks, mean, stdv, cfg.nlat, cfg.nlon, nch, nup, 4, 3, g1.H, g1.W, Ms};
-      EpiStoreF32 es{ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW, ws.skiph, C / 64};
+      EpiStoreF32 es{img_stream ? nullptr : ws.x1, C, embed_s_b, Ms, g1.T, HW, 0, (long long)HW, ws.skiph, C / 64};
       if ((rc = gemm_prod<192>(KT_EMBED, ps, es, embed_s, Ms, ws.scratch, st))) return rc;
     }
     if (stop == 0) return 0;

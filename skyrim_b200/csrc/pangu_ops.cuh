@@ -212,9 +212,11 @@ struct EpiStoreF32 {
           }
         }
         // the lane owns its row: 256-bit stores, one full 32-byte sector per lane and instruction
-        float* o = out + dst * ldo + n0 + c;
+        if (out) {   // null with the image-only token stream: nothing reads the fp32 rows
+          float* o = out + dst * ldo + n0 + c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) stg_f32x8(o + 8 * j, v + 8 * j);
+          for (int j = 0; j < 4; ++j) stg_f32x8(o + 8 * j, v + 8 * j);
+        }
         if (img) {
           const int col = n0 + c;
           uint8_t* base = img + ((size_t)(dst >> 7) * nkb + (col >> 6)) * 16384 + (size_t)(dst & 127) * 128;
