@@ -21,4 +21,14 @@ $NCU --set full -k regex:k_gemm_batched -c 4 -f -o gpurun_out/${tag}_sfno_gb_ful
     python tools/gpu_sfno_one_step.py 1 > gpurun_out/ncu_s2.log 2>&1
 $NCU --set full -k regex:k_gemm_batched --launch-skip 48 -c 3 -f -o gpurun_out/${tag}_sfno_gb2_full \
     python tools/gpu_sfno_one_step.py 1 > gpurun_out/ncu_s3.log 2>&1
+# ---- GraphCast (config 4) and the kernels added late in round 2 (what produced profiles/r2e_* and r2f_*) ----
+$NCU --metrics gpu__time_duration.sum -k regex:"k_gemm|k_gc_" -c 400 --csv --log-file gpurun_out/${tag}_launches_graphcast.csv \
+    python tools/gpu_graphcast_one.py 2 > gpurun_out/ncu_lg.log 2>&1
+$NCU --set full --import-source on -k regex:k_gemm_split --launch-skip 8 -c 1 -f -o gpurun_out/${tag}_gc_ln_edge \
+    python tools/gpu_graphcast_one.py 1 > gpurun_out/ncu_g1.log 2>&1      # mesh-edge LayerNorm GEMM (column-split pair)
+$NCU --set full --import-source on -k regex:k_gemm_pair --launch-skip 2 -c 1 -f -o gpurun_out/${tag}_gc_hidden_edge \
+    python tools/gpu_graphcast_one.py 1 > gpurun_out/ncu_g2.log 2>&1      # mesh-edge hidden GEMM (A-stationary pair, gathers)
+$NCU --set full --import-source on -k regex:k_gemm_split --launch-skip 2 -c 1 -f -o gpurun_out/${tag}_pangu_proj_split \
+    python tools/gpu_one_step.py 1 > gpurun_out/ncu_p.log 2>&1           # Pangu C=384 projection (column-split pair)
+python tools/gpu_graphcast.py 6 > gpurun_out/${tag}_graphcast_families.log 2>&1
 du -sh gpurun_out; ls -la gpurun_out | tail -20
