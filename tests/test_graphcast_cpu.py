@@ -193,3 +193,63 @@ def test_library_exports_graphcast_symbols():
     for name in ("sky_model_set_clock", "sky_toa_radiation"):
         assert hasattr(L, name)
     assert _ffi.SKY_MODEL_GRAPHCAST == 3
+
+
+# -- host logic of the model wrapper on a CPU fake of the stepper protocol --------------------------------------------------
+class _FakeStepper:
+    """stepper protocol of /root/reference/skyrim/core/models/graphcast.py:110,118 on the CPU: new slice = last slice + 1"""
+    def __init__(self, loop):
+        self.loop = loop
+
+    def initialize(self, x, time):
+        return (time, x.float().clone(), None)
+
+    def step(self, state):
+        time, fields, rng = state
+        new = torch.stack([fields[:, 1], fields[:, 1] + 1.0], dim=1)
+        return (time + self.loop.time_step, new, rng), new[:, -1]
+
+
+class _FakeLoop:
+    import datetime as _dt
+    n_history_levels = 2
+    time_step = _dt.timedelta(hours=6)
+    channel_names = in_channel_names = out_channel_names = GRAPHCAST_CHANNELS
+    device = torch.device("cpu")
+
+    def __init__(self, nlat=9, nlon=16):
+        from skyrim_b200.timeloop import equiangular_grid
+        self.grid = equiangular_grid(nlat, nlon)
+        self.stepper = _FakeStepper(self)
+
+    def fill_forcing(self, x, time):
+        x[:, :, -1] = 7.0
+        return x
+
+
+def test_graphcast_model_host_logic_on_a_fake_stepper(tmp_path):
+    """rollout / forecast / predict_one_step of GraphcastModel (time coordinates, two-slice files, channel names) without a GPU"""
+    import datetime
+    from skyrim_b200 import xr_shim as xr
+    from skyrim_b200.core.models.graphcast import GraphcastModel
+
+    class Fake(GraphcastModel):
+        def build_model(self):
+            return _FakeLoop(self._cfg.nlat, self._cfg.nlon)
+
+    m = Fake(ic_source="synthetic", cfg=graphcast_small(9, 16, 1, 512, 1))
+    assert m.time_steps(13) == 2 and set(m.out_channel_names) == set(GRAPHCAST_CHANNELS)
+    t0 = datetime.datetime(2024, 4, 4)
+    pred, paths = m.rollout(t0, n_steps=3, save=True, save_config=dict(output_dir=str(tmp_path), file_type="netcdf"))
+    assert pred.shape == (2, 83, 9, 16) and len(paths) == 3
+    assert [str(t)[:13] for t in pred.coords["time"]] == ["2024-04-04T12", "2024-04-04T18"]
+    np.testing.assert_allclose(pred.values[1], pred.values[0] + 1.0)
+    assert paths[0].split("/")[-1].startswith("graphcast__synthetic__20240404_00:00__20240404_06:00")
+    assert paths[1].split("/")[-1].startswith("graphcast__file__20240404_06:00__20240404_12:00")
+    back = xr.open_dataarray(paths[2])
+    np.testing.assert_array_equal(back.values, pred.values)
+    f = m.forecast(t0, n_steps=2, channels=["t2m", "tp06"])
+    assert f.shape == (3, 2, 9, 16) and list(f.coords["channel"]) == ["t2m", "tp06"]
+    assert float(f.values[0, 1].max()) == 7.0, "the forcing channel of the initial condition was filled through the time loop"
+    one = m.predict_one_step(t0)
+    np.testing.assert_allclose(one.values[1], one.values[0] + 1.0)
