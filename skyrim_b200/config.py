@@ -1,4 +1,4 @@
-"""Shape configuration of the two step operators on the hot path.
+"""Shape configuration of the step operators on the hot path (Pangu-Weather, FourCastNet-v2 SFNO, GraphCast).
 
 The reference carries no architecture description of its own: the
 arithmetic lives in ONNX graphs / earth2mip modules it downloads.  The numbers below
