@@ -5,9 +5,10 @@
 // field (graphcast.py:17-41; 82 prognostic channels + the toa-radiation forcing the reference labels "tp06").
 // One step = encoder (grid -> mesh), 16 message-passing layers on the multimesh, decoder (mesh -> grid), residual update.
 //
-// B200 mapping.  Every MLP is two persistent TMA-fed tcgen05 GEMMs (k_gemm2): hidden = swish(A W1^T + ...) written as the
-// fp16 operand image of the second GEMM, whose epilogue does bias + LayerNorm (+ residual) and writes the operand image
-// of whatever consumes it next.  The concatenations of the published formulation never exist:
+// B200 mapping.  Every MLP is two persistent TMA-fed tcgen05 GEMMs: hidden = swish(A W1^T + ...) (k_gemm_pair: A-stationary
+// CTA pairs, cta_group::2; k_gemm2 where K != 512) written as the fp16 operand image of the second GEMM (k_gemm_split:
+// column-split CTA pairs, LayerNorm statistics over DSMEM), whose epilogue does bias + LayerNorm (+ residual, read from the
+// stream's own fp16 image for grid nodes and mesh edges) and writes the operand image of whatever consumes it next.  The concatenations of the published formulation never exist:
 //   * [edge, sender, receiver] W1^T = edge W1e^T + (v W1s^T)[sender] + (v W1r^T)[receiver]: the per-NODE products are
 //     small GEMMs into fp16 tables, gathered by edge index inside the hidden GEMM's epilogue (row-owner lanes);
 //   * [node, sum of incoming edges] is a K-concatenation of two operand images (AImage), the sum produced by a

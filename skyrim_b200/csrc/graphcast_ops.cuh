@@ -2,9 +2,10 @@
 // builder, the CSR aggregation and small set-up kernels.  Latent width is fixed at 512 (GC_L).
 //
 // Data layout (per member): every latent matrix (grid nodes, mesh nodes, the three edge sets) is an fp16 tile image
-// [rows/128][8][128 x 128 B, SWIZZLE_128B] — byte for byte the A operand of the next GEMM — plus, for the three residual
-// streams (grid nodes, mesh nodes, mesh edges), an fp32 row-major copy.  Per-node first-layer partial products
-// ("tables": v W1_s^T, v W1_r^T) are fp16 row-major and are gathered by edge index inside the hidden GEMM's epilogue.
+// [rows/128][8][128 x 128 B, SWIZZLE_128B] — byte for byte the A operand of the next GEMM.  Of the three residual streams
+// only the mesh nodes keep an fp32 row-major copy; grid nodes and mesh edges are read-modify-written in their images
+// (EpiGcLn<2>).  Per-node first-layer partial products ("tables": v W1_s^T, v W1_r^T) are fp16 row-major and are gathered
+// by edge index inside the hidden GEMM's epilogue.
 #pragma once
 #include "gemm2.cuh"
 
