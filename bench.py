@@ -35,7 +35,7 @@ METRIC = "6h rollout steps/sec on (69,721,1440); ensemble member-steps/sec @1/2/
 UNIT = "member-steps/s"
 VERIFY_TOL = 1e-3      # per-channel relative L2 on the point sample (north star); block means / RMS in sigma units below
 VERIFY_TOL_SIGMA = 5e-3
-VERIFY_TOL_TENDENCY = 2e-2   # GraphCast: per-channel relative L2 of the network tendency (state = x + 0.1 sigma x tendency)
+VERIFY_TOL_TENDENCY = 4e-3   # GraphCast: per-channel relative L2 of the network tendency (state = x + 0.1 sigma x tendency); measured 1.4e-3
 
 
 def _peaks():

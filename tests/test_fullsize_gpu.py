@@ -118,7 +118,7 @@ def test_graphcast_full_size_oracle_parity():
           f"norm {s['norm']:.3e}; tendency: rel {s['t_rel']:.3e} block {s['t_block']:.3e} norm {s['t_norm']:.3e}")
     assert s["finite"] and s["slice0_is_old_slice1"]
     assert s["rel"] < TOL and s["norm"] < TOL and s["nrm"] < TOL_SIGMA and s["block"] < TOL_SIGMA and s["last"] < TOL_SIGMA
-    assert s["t_rel"] < 2e-2 and s["t_norm"] < 5e-3, "tendency (network output) error"
+    assert s["t_rel"] < 4e-3 and s["t_norm"] < 2e-3, "tendency (network output) error (measured 1.4e-3 / 5.1e-4)"
     eng.close()
 
 

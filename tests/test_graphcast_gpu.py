@@ -2,8 +2,8 @@
 (oracle/graphcast_ref.py) on the same seeded weights, graph tables and initial condition.
 
 Tolerances: the north star's per-channel relative error <= 1e-3 on the stepped STATE, and — stricter in effect, because
-the state is x + 0.1 sigma * tendency — a relative error <= 2e-2 per channel on the network's TENDENCY itself (fp16 tensor-core
-operands through 2 + 2 x layers + 2 LayerNorm-ed MLPs; the oracle's own fp16-operand emulation gives the same figure).
+the state is x + 0.1 sigma * tendency — a relative error <= 4e-3 per channel on the network's TENDENCY itself (fp16 tensor-core
+operands through 2 + 2 x layers + 2 LayerNorm-ed MLPs: measured 1.2e-3 .. 1.4e-3, what the oracle's own fp16 emulation gives).
 """
 import datetime
 
@@ -19,7 +19,7 @@ from skyrim_b200.weights import make_graphcast_weights, synthetic_graphcast_stat
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3        # per-channel relative error of the state (north star)
-TOL_TEND = 2e-2   # per-channel relative error of the tendency (network output)
+TOL_TEND = 4e-3   # per-channel relative error of the tendency (network output); measured 1.2e-3 .. 1.4e-3
 T0 = 1714521600.0  # 2024-05-01T00:00:00Z
 
 
