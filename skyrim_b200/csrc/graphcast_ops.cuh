@@ -266,7 +266,7 @@ struct EpiGcLn {
                      "f"(s), "f"(ss), "r"(e.x_peer_bar)
                      : "memory");
       }
-      mbar_wait_cluster(e.x_own_bar, e.x_parity);
+      mbar_wait(e.x_own_bar, e.x_parity);   // CTA-scope acquire: the peer's sums arrive in THIS CTA's shared memory through st.async, whose completion the barrier phase carries (as for bulk copies); the cluster-scope wait added an L1 invalidate (CCTL.IVALL) per tile
       float ps, pss;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps), "=f"(pss) : "r"(e.x_own_stat + e.lane * 8));
       s += ps; ss += pss;
