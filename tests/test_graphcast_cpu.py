@@ -253,3 +253,19 @@ def test_graphcast_model_host_logic_on_a_fake_stepper(tmp_path):
     assert float(f.values[0, 1].max()) == 7.0, "the forcing channel of the initial condition was filled through the time loop"
     one = m.predict_one_step(t0)
     np.testing.assert_allclose(one.values[1], one.values[0] + 1.0)
+
+
+def test_roofline_accounting_of_the_engine_formulation():
+    """bench.py's per-family roofline for configs.graphcast: FLOPs and mandatory HBM bytes of the step as the engine runs it
+    (first layers split per input, fp16-only grid-node / mesh-edge streams) — DESIGN.md section 4c quotes these figures"""
+    from skyrim_b200 import roofline as R
+    cfg = graphcast_full()
+    fl, by = R.graphcast_flops(cfg), R.graphcast_bytes(cfg)
+    assert abs(fl["total"] - 17.46e12) < 0.1e12 and abs(by["total"] - 100.5e9) < 1.5e9, (fl["total"], by["total"])
+    assert fl["gc_hidden"] > fl["gc_ln"] > fl["gc_table"] > fl["gc_out"] > 0 and fl["gc_agg"] == 0
+    naive = 2.0 * 512 * (cfg.n_grid * (184 + 512) + 1629780 * 4 * 512 + 40962 * 3 * 512 + cfg.n_grid * 2 * 512
+                         + 16 * (327660 * 4 * 512 + 40962 * 3 * 512) + 3 * cfg.n_grid * 4 * 512 + cfg.n_grid * 3 * 512 + cfg.n_grid * 512)
+    assert naive > 1.4 * fl["total"], "the published concatenated formulation needs ~1.5 x the engine's FLOPs"
+    small_cfg = graphcast_small(41, 96, 2, 512, 2)
+    g = icomesh.build_graph(41, 96, 2)
+    assert R.graphcast_flops(small_cfg, g)["total"] < 1e11
