@@ -60,6 +60,7 @@ struct GraphCastEngine : Engine {
   float* vm0_f32 = nullptr;
   __half* g2m_tr = nullptr;             // (Nm, 512): embedded mesh nodes x W1r(g2m_edge)^T
   bool use_pair = true;   // debug_set("gc_pair", 0): hidden GEMMs on k_gemm2 (A/B timing, bisection)
+  cudaStream_t prep_stream = nullptr;   // stream of the running prepare() (dalloc's zero fills)
   bool l2_prefetch = true;  // debug_set("gc_prefetch", 0)
   bool use_split = true;  // debug_set("gc_split", 0): LayerNorm GEMMs on k_gemm2 with one 512-column accumulator
   // clock
@@ -79,7 +80,8 @@ struct GraphCastEngine : Engine {
   T* dalloc(size_t n, bool zero = false) {
     void* p = nullptr;
     if (cudaMalloc(&p, n * sizeof(T) + 16) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", n * sizeof(T)); return nullptr; }
-    if (zero) cudaMemset(p, 0, n * sizeof(T) + 16);
+    // zero-fill on the stream the packing kernels run on (a legacy-stream cudaMemset is not ordered against a non-blocking stream)
+    if (zero) cudaMemsetAsync(p, 0, n * sizeof(T) + 16, prep_stream);
     owned.push_back(p);
     return reinterpret_cast<T*>(p);
   }
@@ -269,6 +271,7 @@ struct GraphCastEngine : Engine {
   }
 
   int prepare(cudaStream_t st) override {
+    prep_stream = st;
     if (cfg.latent != GC_L) { set_error("GraphCast engine is built for latent %d", GC_L); return SKY_ERR_ARG; }
     if (nfeat > GC_FEAT_KP || cfg.n_state != cfg.n_prog + 1) { set_error("unsupported GraphCast channel layout"); return SKY_ERR_ARG; }
     const int L = GC_L;
